@@ -1,0 +1,181 @@
+/*
+ * wfcrl_b200 -- C-ABI of the B200-native batched Floris backend for ifpen/wfcrl-env.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference: everything that happens behind
+ * `FlorisInterface.update_command` (reference wfcrl/interface.py:557-586) for every `*_Floris` env step, i.e. the
+ * FLORIS 3.5 GCH steady-state wake solve, the per-turbine measures (interface.py:622-648) and -- fused around it --
+ * the WFCRL MDP transition and reward (wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/rewards.py:16-46),
+ * evaluated for `num_envs` independent environments at once by hand-written sm_100a CUDA kernels.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; every function returns WF_OK (0) or an error code and
+ *    never throws; `wf_last_error()` returns a thread-local human-readable message.
+ *  - "real" = double when the handle was created with WF_PREC_F64 (bit-check mode, <=1e-9 relative vs the
+ *    reference arithmetic) and float with WF_PREC_F32 (fast mode, <=1e-4 relative).
+ *  - all `d_*` pointers are DEVICE pointers on the handle's device, all `h_*` pointers are HOST pointers.
+ *  - per-turbine arrays are row-major [num_envs][num_turbines] in the ORIGINAL turbine order of the layout.
+ *  - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*; NULL = default
+ *    stream); no host synchronisation happens inside unless stated.
+ *  - there is NO CPU fallback: without a CUDA device `wf_create` fails with WF_ERR_CUDA.
+ */
+#ifndef WFCRL_B200_H
+#define WFCRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_MAX_TURBINES 128 /* one thread per turbine inside a CTA */
+#define WF_TABLE_MAX 64     /* rows of the Cp/Ct table (nrel_5MW has 51) */
+
+typedef struct WfHandle_t* WfHandle;
+
+enum WfStatus { WF_OK = 0, WF_ERR_INVALID = 1, WF_ERR_CUDA = 2, WF_ERR_NOMEM = 3 };
+enum WfPrecision { WF_PREC_F64 = 0, WF_PREC_F32 = 1 };
+/* reward shapers of wfcrl/rewards.py:16-46 */
+enum WfShaper { WF_SHAPER_NONE = 0, WF_SHAPER_REFERENCE_PCT = 1, WF_SHAPER_STEP_PCT = 2 };
+/* kernel variants: 0 = straightforward one-thread-per-turbine kernel (FP64 and FP32), 1 = tuned FP32 kernel */
+enum WfKernel { WF_KERNEL_BASIC = 0, WF_KERNEL_FAST = 1 };
+
+/*
+ * Everything the reference reads from its FlorisCase / case.yaml / env kwargs for this path.
+ * `wf_default_config` fills the values of wfcrl/simulators/floris/inputs/template/case.yaml:14-16,27-39,41-60,84-89,
+ * FLORIS' turbine_library nrel_5MW and the env defaults of wfcrl/simple_env.py:24-25,
+ * wfcrl/environments/data_cases.py:19-23 (yaw bounds), wfcrl/mdp.py:52 (actuator rate).
+ */
+typedef struct WfConfig {
+    int32_t num_turbines;       /* T <= WF_MAX_TURBINES */
+    int32_t num_envs;           /* B: environments resident on this device (the local shard) */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t precision;          /* enum WfPrecision */
+    int32_t kernel;             /* enum WfKernel (WF_KERNEL_FAST requires WF_PREC_F32) */
+    int32_t max_iter;           /* interface.max_iter = start_iter + max_num_steps (simple_env.py:33, interface.py:586) */
+    int32_t continuous_control; /* mdp.py:300-310: 1 = Box actions clipped to +-step, 0 = {0,1,2} -> (a-1)*step */
+    int32_t multi_agent;        /* 1 = actuation constraint with the per-agent staleness of multiagent_env.py:198-249 */
+    int32_t reward_shaper;      /* enum WfShaper */
+    int32_t reserved0;
+    double yaw_lo, yaw_hi, yaw_step; /* controls["yaw"] = (low, high, step), default (-40, 40, 5) */
+    double load_coef;                /* simple_env.py:25 */
+    double shaper_reference;         /* ReferencePercentage.reference / StepPercentage initial reference */
+    double dt;                       /* FlorisCase.dt = 60 (data_cases.py:507) */
+    double actuator_rate;            /* mdp.py:52 ACTUATORS_RATE["yaw"] = 0.3 */
+    /* flow field (case.yaml:30-39) */
+    double air_density, turbulence_intensity, wind_shear, wind_veer;
+    /* Gauss deflection / velocity parameters (case.yaml:52-60, 76-80) */
+    double alpha, beta, ka, kb, ad, bd, dm;
+    /* Crespo-Hernandez (case.yaml:84-89) */
+    double ch_initial, ch_constant, ch_ai, ch_downstream;
+    /* turbine (nrel_5MW) */
+    double rotor_diameter, hub_height, tsr, pP, pT, generator_efficiency, ref_density_cp_ct;
+    int32_t table_len;
+    int32_t reserved1;
+    double table_ws[WF_TABLE_MAX], table_cp[WF_TABLE_MAX], table_ct[WF_TABLE_MAX];
+} WfConfig;
+
+/*
+ * Device output buffers of one step; any pointer may be NULL (that output is skipped).
+ * Replaces what the reference returns from WindFarmEnv.step (simple_env.py:86-96):
+ *   yaw, wind_speed, wind_direction, freewind -> the observation dict (mdp.py:278-281)
+ *   power [MW] and load -> info["power"], info["load"] (mdp.py:282-284)
+ *   reward -> simple_env.py:78-85 ; truncated -> interface.py:586 ; terminated is always false (simple_env.py:87)
+ */
+typedef struct WfStepOut {
+    void* yaw;            /* real [B][T]    yaw state after the transition, degrees */
+    void* wind_speed;     /* real [B][T]    cbrt(mean(u^3)) per rotor           (interface.py:643) */
+    void* wind_direction; /* real [B][T]    mean(wd - degrees(atan2(v,u)))      (interface.py:644-647) */
+    void* power;          /* real [B][T]    MW in env mode (mdp.py:284), W in interface mode (interface.py:623) */
+    void* load;           /* real [B][T][4] TI, std u, std v, std w (interface.py:629-637); env mode: x1e7 then /1e7,
+                                            interface mode: x1e7 as stored in current_measures (interface.py:575-577) */
+    void* reward;         /* real [B]       env mode only */
+    void* freewind;       /* real [B][2]    free-stream wind speed, direction (interface.py:625-627) */
+    uint8_t* truncated;   /* [B]            _num_iter == max_iter (interface.py:586) */
+} WfStepOut;
+
+/* Host mirror of WfStepOut for the end-to-end entry point (pinned or pageable host memory, same shapes). */
+typedef WfStepOut WfHostOut;
+
+/* Fill `cfg` with the reference defaults (see WfConfig). num_turbines / num_envs / max_iter are left 0. */
+int wf_default_config(WfConfig* cfg);
+
+/*
+ * Replaces FlorisInterface.from_case / __init__ (interface.py:462-501, 526-547) and WindFarmMDP.__init__'s
+ * accumulators (mdp.py:157-160) for `num_envs` envs sharing one layout.  layout_x/y: HOST, [T] metres.
+ * All envs start with wind (8 m/s, 270 deg) (data_cases.py:99-100), zero yaw, zero counters.
+ */
+int wf_create(const WfConfig* cfg, const double* h_layout_x, const double* h_layout_y, WfHandle* out);
+int wf_destroy(WfHandle h);
+
+/*
+ * Replaces WindFarmMDP.reset -> FlorisInterface.init + (start_iter+1) x update_command() (mdp.py:260-270,
+ * interface.py:588-613): for the selected envs set the wind, zero yaw / accumulators / iteration counters / shaper
+ * state, rebuild the rotated + sorted geometry and run `warmup_solves` zero-yaw solves (each increments _num_iter,
+ * which is why an env with max_num_steps=N truncates at step N-1).  `out` receives the start observation rows of
+ * the selected envs (other rows untouched).
+ *   h_env_ids : HOST int32 [n] or NULL with n == num_envs meaning "all envs in order"
+ *   h_ws, h_wd: HOST double [n] wind speed [m/s] and direction [deg] (wd is reduced % 360 as interface.py:664)
+ *   h_cos, h_sin: HOST double [n] or NULL.  When given they are used as cosd/sind of the wind deviation from west
+ *                 instead of the device's own FP64 cos/sin (bit-exact geometry vs a host reference).
+ */
+int wf_reset(WfHandle h, const int32_t* h_env_ids, int32_t n, const double* h_ws, const double* h_wd,
+             const double* h_cos, const double* h_sin, int32_t warmup_solves, const WfStepOut* out, void* stream);
+
+/* Same as wf_reset but fully on device: d_mask uint8 [B] selects envs, d_ws/d_wd double [B] (read where mask!=0). */
+int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd,
+                    int32_t warmup_solves, const WfStepOut* out, void* stream);
+
+/*
+ * ENV MODE.  Replaces one WindFarmEnv.step / one full MAWindFarmEnv agent cycle for every env:
+ * actuation-rate constraint (simple_env.py:65-72), action clip + yaw transition in float32 + accumulator
+ * (mdp.py:291-319), FlorisInterface.update_command (interface.py:557-586), powers/1e6 and loads/1e7
+ * (mdp.py:278-284), reward with the previous state's free-stream speed (simple_env.py:78-85) and the shaper.
+ *   d_action: DEVICE float [B][T]; continuous: yaw increments in degrees; discrete: values in {0,1,2}.
+ */
+int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream);
+
+/*
+ * INTERFACE MODE.  Replaces FlorisInterface.update_command(yaw=...) (interface.py:557-586) alone: no constraint, no
+ * clipping, no reward.  d_yaw: DEVICE double [B][T] absolute yaw command in degrees, or NULL to keep the current
+ * command (update_command() with no argument, mdp.py:262).
+ */
+int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, void* stream);
+
+/*
+ * End-to-end convenience for hosts without device buffers: copies `h_action` (float [B][T]) host->device, runs
+ * wf_step, copies every non-NULL member of `h_out` device->host and synchronises the stream.  Uses pinned staging
+ * owned by the handle.  h2d/d2h bytes moved are returned through the optional counters.
+ */
+int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* h_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* Change per-env wind without resetting counters (FlorisInterface.update_wind, interface.py:663-671; time-series
+ * mode).  Rebuilds the geometry of the selected envs. d_mask may be NULL (= all). */
+int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, void* stream);
+
+/* Per-env ambient turbulence intensity (extension; the reference keeps case.yaml's 0.06). d_ti: double [B]. */
+int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);
+
+/*
+ * State access for tests / checkpoint-resume (synchronous).  `name` is one of
+ *   "yaw" f64[B][T] | "acc" f32[B][T] | "acc_prev" f32[B][T] | "num_iter" i32[B] | "num_moves" i32[B] |
+ *   "ws" f64[B] | "wd" f64[B] | "ws_norm" f64[B] | "shaper_ref" f64[B] | "ti_ambient" f64[B] |
+ *   "order" i32[B][T] | "xs" f64[B][T] | "ys" f64[B][T] | "xi" f64[B][T] | "yi" f64[B][T] | "cs" f64[B][2]
+ * `bytes` must equal the full array size.
+ */
+int wf_get_state(WfHandle h, const char* name, void* h_dst, size_t bytes);
+int wf_set_state(WfHandle h, const char* name, const void* h_src, size_t bytes);
+
+/* Introspection for bench.py: SM count of the device, and occupancy facts of the step kernel in use. */
+int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t* ctas_per_sm,
+                   int32_t* regs_per_thread, int32_t* threads_per_cta, int32_t* smem_per_cta);
+/* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+uint64_t wf_launch_count(WfHandle h);
+
+const char* wf_last_error(void);
+const char* wf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFCRL_B200_H */

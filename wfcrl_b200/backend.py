@@ -1,0 +1,194 @@
+"""``FlorisBatch``: thin PyTorch-facing wrapper over the C-ABI (device memory, streams; no arithmetic here).
+
+It replaces, for ``num_envs`` environments at once, what the reference reaches through
+``FlorisInterface`` (wfcrl/interface.py:444-671) plus the MDP transition / reward wrapped around it
+(wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96).  All compute happens in libwfcrl_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PREC = {"f64": _lib.PREC_F64, "fp64": _lib.PREC_F64, "f32": _lib.PREC_F32, "fp32": _lib.PREC_F32}
+_KERN = {"basic": _lib.KERNEL_BASIC, "fast": _lib.KERNEL_FAST}
+_SHAPER = {"none": _lib.SHAPER_NONE, "reference": _lib.SHAPER_REFERENCE_PCT, "step": _lib.SHAPER_STEP_PCT}
+
+_STATE_DTYPES = {
+    "yaw": (np.float64, "BT"), "acc": (np.float32, "BT"), "acc_prev": (np.float32, "BT"),
+    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
+    "ws_norm": (np.float64, "B"), "shaper_ref": (np.float64, "B"), "ti_ambient": (np.float64, "B"),
+    "order": (np.int32, "BT"), "xs": (np.float64, "BT"), "ys": (np.float64, "BT"), "xi": (np.float64, "BT"),
+    "yi": (np.float64, "BT"), "cs": (np.float64, "B2"),
+}
+
+
+def default_config() -> _lib.WfConfig:
+    cfg = _lib.WfConfig()
+    _lib.check(_lib.load().wf_default_config(C.byref(cfg)))
+    return cfg
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class FlorisBatch:
+    """``num_envs`` independent Floris-backed wind-farm envs sharing one layout, resident on one GPU."""
+
+    def __init__(self, layout_x: Sequence[float], layout_y: Sequence[float], num_envs: int, *, device: int = 0,
+                 precision: str = "f64", kernel: str = "basic", max_iter: int = 500,
+                 yaw_bounds=(-40.0, 40.0, 5.0), load_coef: float = 0.1, reward_shaper: str = "none",
+                 shaper_reference: float = 0.0, continuous_control: bool = True, multi_agent: bool = False,
+                 config_overrides: Optional[Dict[str, float]] = None):
+        if not torch.cuda.is_available():
+            raise _lib.WfError("wfcrl_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.T = len(layout_x)
+        self.B = int(num_envs)
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        self.real = torch.float64 if _PREC[precision] == _lib.PREC_F64 else torch.float32
+        cfg = default_config()
+        cfg.num_turbines, cfg.num_envs, cfg.device = self.T, self.B, device
+        cfg.precision, cfg.kernel = _PREC[precision], _KERN[kernel]
+        cfg.max_iter = int(max_iter)
+        cfg.continuous_control = int(bool(continuous_control))
+        cfg.multi_agent = int(bool(multi_agent))
+        cfg.reward_shaper = _SHAPER[reward_shaper]
+        cfg.shaper_reference = float(shaper_reference)
+        cfg.yaw_lo, cfg.yaw_hi, cfg.yaw_step = (float(v) for v in yaw_bounds)
+        cfg.load_coef = float(load_coef)
+        for key, val in (config_overrides or {}).items():
+            if not hasattr(cfg, key):
+                raise ValueError(f"unknown config field {key}")
+            setattr(cfg, key, val)
+        self.cfg = cfg
+        lx = np.ascontiguousarray(layout_x, dtype=np.float64)
+        ly = np.ascontiguousarray(layout_y, dtype=np.float64)
+        handle = C.c_void_p()
+        _lib.check(self.lib.wf_create(C.byref(cfg), lx.ctypes.data_as(C.c_void_p), ly.ctypes.data_as(C.c_void_p),
+                                      C.byref(handle)))
+        self.handle = handle
+        B, T, dev, r = self.B, self.T, self.device, self.real
+        self.out = {
+            "yaw": torch.zeros(B, T, dtype=r, device=dev),
+            "wind_speed": torch.zeros(B, T, dtype=r, device=dev),
+            "wind_direction": torch.zeros(B, T, dtype=r, device=dev),
+            "power": torch.zeros(B, T, dtype=r, device=dev),
+            "load": torch.zeros(B, T, 4, dtype=r, device=dev),
+            "reward": torch.zeros(B, dtype=r, device=dev),
+            "freewind": torch.zeros(B, 2, dtype=r, device=dev),
+            "truncated": torch.zeros(B, dtype=torch.uint8, device=dev),
+        }
+        self._out_struct = _lib.WfStepOut(*[self.out[k].data_ptr() for k in
+                                            ("yaw", "wind_speed", "wind_direction", "power", "load", "reward",
+                                             "freewind", "truncated")])
+        self._host = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.wf_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------------------
+    def reset(self, wind_speed, wind_direction, env_ids=None, *, host_trig: bool = True, warmup_solves: int = 1):
+        """WindFarmMDP.reset for the selected envs (mdp.py:260-270).  ``host_trig=True`` ships numpy's FP64 cosd/sind of
+        the wind deviation so the rotated geometry is bit-identical to a host (numpy) reference."""
+        ids = np.arange(self.B, dtype=np.int32) if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        n = ids.shape[0]
+        ws = np.ascontiguousarray(np.broadcast_to(np.asarray(wind_speed, dtype=np.float64), (n,)))
+        wd = np.ascontiguousarray(np.broadcast_to(np.asarray(wind_direction, dtype=np.float64), (n,)))
+        hc = hs = None
+        if host_trig:
+            dev = (((wd % 360.0) - 270.0) % 360.0 + 360.0) % 360.0
+            hc = np.ascontiguousarray(np.cos(np.radians(dev)))
+            hs = np.ascontiguousarray(np.sin(np.radians(dev)))
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(self.lib.wf_reset(self.handle, vp(ids), n, vp(ws), vp(wd), vp(hc), vp(hs), int(warmup_solves),
+                                     C.byref(self._out_struct), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # host staging arrays above must outlive the copies
+        return self.out
+
+    def reset_masked(self, mask: torch.Tensor, wind_speed: torch.Tensor, wind_direction: torch.Tensor,
+                     warmup_solves: int = 1):
+        """Device-side reset of the envs where ``mask`` (uint8 [B]) is non-zero; no host round trip."""
+        assert mask.dtype == torch.uint8 and wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64
+        _lib.check(self.lib.wf_reset_masked(self.handle, _ptr(mask), _ptr(wind_speed), _ptr(wind_direction),
+                                            int(warmup_solves), C.byref(self._out_struct), self._stream()))
+        return self.out
+
+    def step(self, action: torch.Tensor):
+        """One env step for every env; ``action`` float32 [B, T] on the device.  Returns the output tensor dict
+        (overwritten in place every call)."""
+        assert action.dtype == torch.float32 and action.is_cuda and action.is_contiguous()
+        assert action.shape == (self.B, self.T)
+        _lib.check(self.lib.wf_step(self.handle, _ptr(action), C.byref(self._out_struct), self._stream()))
+        return self.out
+
+    def update_command(self, yaw: Optional[torch.Tensor] = None):
+        """FlorisInterface.update_command(yaw) for every env (interface.py:557-586); power in W, loads x1e7."""
+        if yaw is not None:
+            assert yaw.dtype == torch.float64 and yaw.is_cuda and yaw.is_contiguous() and yaw.shape == (self.B, self.T)
+        _lib.check(self.lib.wf_update_command(self.handle, _ptr(yaw), C.byref(self._out_struct), self._stream()))
+        return self.out
+
+    def step_host(self, action_host: torch.Tensor, fields=("yaw", "wind_speed", "wind_direction", "reward",
+                                                           "truncated", "power", "load", "freewind")):
+        """End-to-end step from HOST memory (pinned recommended): H2D action, step, D2H of ``fields``, sync."""
+        assert action_host.dtype == torch.float32 and not action_host.is_cuda and action_host.is_contiguous()
+        if self._host is None:
+            self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.out.items()}
+        names = ("yaw", "wind_speed", "wind_direction", "power", "load", "reward", "freewind", "truncated")
+        st = _lib.WfStepOut(*[(self._host[k].data_ptr() if k in fields else None) for k in names])
+        up, down = C.c_uint64(), C.c_uint64()
+        _lib.check(self.lib.wf_step_host(self.handle, C.c_void_p(action_host.data_ptr()), C.byref(st), C.byref(up),
+                                         C.byref(down)))
+        self.last_h2d_bytes, self.last_d2h_bytes = up.value, down.value
+        return {k: self._host[k] for k in fields}
+
+    def set_turbulence_intensity(self, ti: torch.Tensor):
+        assert ti.dtype == torch.float64 and ti.is_cuda and ti.shape == (self.B,)
+        _lib.check(self.lib.wf_set_turbulence_intensity(self.handle, _ptr(ti), self._stream()))
+
+    def update_wind(self, wind_speed: torch.Tensor, wind_direction: torch.Tensor):
+        assert wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64
+        _lib.check(self.lib.wf_update_wind(self.handle, None, _ptr(wind_speed), _ptr(wind_direction), self._stream()))
+
+    # ------------------------------------------------------------------------------------------------------
+    def _shape(self, kind):
+        return {"BT": (self.B, self.T), "B": (self.B,), "B2": (self.B, 2)}[kind]
+
+    def get_state(self, name: str) -> np.ndarray:
+        dt, kind = _STATE_DTYPES[name]
+        arr = np.empty(self._shape(kind), dtype=dt)
+        _lib.check(self.lib.wf_get_state(self.handle, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return arr
+
+    def set_state(self, name: str, value) -> None:
+        dt, kind = _STATE_DTYPES[name]
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), self._shape(kind)))
+        _lib.check(self.lib.wf_set_state(self.handle, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def device_info(self) -> Dict[str, int]:
+        vals = [C.c_int32() for _ in range(6)]
+        _lib.check(self.lib.wf_device_info(self.handle, *[C.byref(v) for v in vals]))
+        keys = ("sm_count", "sm_clock_khz", "ctas_per_sm", "regs_per_thread", "threads_per_cta", "smem_per_cta")
+        return {k: v.value for k, v in zip(keys, vals)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.wf_launch_count(self.handle))

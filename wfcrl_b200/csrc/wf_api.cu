@@ -1,0 +1,433 @@
+// C-ABI of libwfcrl_b200.so (see include/wfcrl_b200.h).  Host-side only: owns device state, stages inputs and launches
+// the kernels of wf_kernels.cu / wf_fast.cu.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include "../../include/wfcrl_b200.h"
+#include "wf_device.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+// tuned FP32 kernel (wf_fast.cu)
+cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
+                                const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out, int sm_count,
+                                cudaStream_t stream);
+cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+                                    int* smem);
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return set_err(WF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+struct WfHandle_t {
+    WfConfig cfg;
+    WfModel model;
+    WfState st;
+    int device = 0;
+    int sm_count = 0, sm_clock_khz = 0;
+    size_t es = 8;  // element size of "real"
+    std::vector<void*> allocs;
+    // staging for wf_reset (host ids -> dense device arrays)
+    uint8_t* d_mask = nullptr;
+    double *d_rws = nullptr, *d_rwd = nullptr, *d_rcs = nullptr;
+    uint8_t* h_mask = nullptr;
+    double *h_rws = nullptr, *h_rwd = nullptr, *h_rcs = nullptr;
+    // staging for wf_step_host
+    float* d_action = nullptr;
+    WfOutPtrs d_out = {};
+    cudaStream_t host_stream = nullptr;
+    uint64_t launches = 0;
+};
+
+template <typename T> static int dev_alloc(WfHandle_t* h, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return set_err(WF_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    e = cudaMemset(q, 0, n * sizeof(T));
+    if (e != cudaSuccess) return set_err(WF_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return WF_OK;
+}
+#define TRY(expr)                 \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != WF_OK) return _r; \
+    } while (0)
+
+extern "C" {
+
+const char* wf_last_error(void) { return g_err.c_str(); }
+const char* wf_version(void) { return "wfcrl_b200 0.1 (sm_100a)"; }
+
+int wf_default_config(WfConfig* c) {
+    if (!c) return set_err(WF_ERR_INVALID, "cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->precision = WF_PREC_F64;
+    c->kernel = WF_KERNEL_BASIC;
+    c->continuous_control = 1;
+    c->reward_shaper = WF_SHAPER_NONE;
+    c->yaw_lo = -40.0; c->yaw_hi = 40.0; c->yaw_step = 5.0;  // data_cases.py:21
+    c->load_coef = 0.1;                                       // simple_env.py:25
+    c->shaper_reference = 0.0;
+    c->dt = 60.0;                                             // data_cases.py:507
+    c->actuator_rate = 0.3;                                   // mdp.py:52
+    c->air_density = 1.225; c->turbulence_intensity = 0.06; c->wind_shear = 0.12; c->wind_veer = 0.0;
+    c->alpha = 0.58; c->beta = 0.077; c->ka = 0.38; c->kb = 0.004; c->ad = 0.0; c->bd = 0.0; c->dm = 1.0;
+    c->ch_initial = 0.1; c->ch_constant = 0.5; c->ch_ai = 0.8; c->ch_downstream = -0.32;
+    c->rotor_diameter = 126.0; c->hub_height = 90.0; c->tsr = 8.0; c->pP = 1.88; c->pT = 1.88;
+    c->generator_efficiency = 1.0; c->ref_density_cp_ct = 1.225;
+    // nrel_5MW power/thrust table as shipped with FLORIS 3.x
+    static const double cp[51] = {
+        0.0, 0.0, 0.0, 0.178085, 0.289075, 0.349022, 0.384728, 0.406059, 0.420228, 0.428823, 0.433873, 0.436223,
+        0.436845, 0.436575, 0.436511, 0.436561, 0.436517, 0.435903, 0.434673, 0.433230, 0.430466, 0.378869, 0.335199,
+        0.297991, 0.266092, 0.238588, 0.214748, 0.193981, 0.175808, 0.159835, 0.145741, 0.133256, 0.122157, 0.112257,
+        0.103399, 0.095449, 0.088294, 0.081836, 0.075993, 0.070692, 0.065875, 0.061484, 0.057476, 0.053809, 0.050447,
+        0.047358, 0.044518, 0.041900, 0.039483, 0.0, 0.0};
+    static const double ct[51] = {
+        0.0, 0.0, 0.0, 0.99, 0.99, 0.97373036, 0.92826162, 0.89210543, 0.86100905, 0.835423, 0.81237673, 0.79225789,
+        0.77584769, 0.7629228, 0.76156073, 0.76261984, 0.76169723, 0.75232027, 0.74026851, 0.72987175, 0.70701647,
+        0.54054532, 0.45509459, 0.39343381, 0.34250785, 0.30487242, 0.27164979, 0.24361964, 0.21973831, 0.19918151,
+        0.18131868, 0.16537679, 0.15103727, 0.13998636, 0.1289037, 0.11970413, 0.11087113, 0.10339901, 0.09617888,
+        0.09009926, 0.08395078, 0.0791188, 0.07448356, 0.07050731, 0.06684119, 0.06345518, 0.06032267, 0.05741999,
+        0.05472609, 0.0, 0.0};
+    c->table_len = 51;
+    c->table_ws[0] = 0.0; c->table_ws[1] = 2.0; c->table_ws[2] = 2.5;
+    for (int i = 0; i < 45; ++i) c->table_ws[3 + i] = 3.0 + 0.5 * i;
+    c->table_ws[48] = 25.01; c->table_ws[49] = 25.02; c->table_ws[50] = 50.0;
+    for (int i = 0; i < 51; ++i) { c->table_cp[i] = cp[i]; c->table_ct[i] = ct[i]; }
+    return WF_OK;
+}
+
+int wf_destroy(WfHandle h) {
+    if (!h) return WF_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_mask) cudaFreeHost(h->h_mask);
+    if (h->h_rws) cudaFreeHost(h->h_rws);
+    if (h->h_rwd) cudaFreeHost(h->h_rwd);
+    if (h->h_rcs) cudaFreeHost(h->h_rcs);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+    return WF_OK;
+}
+
+int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle* out) {
+    if (!cfg || !lx || !ly || !out) return set_err(WF_ERR_INVALID, "NULL argument");
+    const int T = cfg->num_turbines, B = cfg->num_envs;
+    if (T < 1 || T > WF_MAX_TURBINES) return set_err(WF_ERR_INVALID, "num_turbines must be in [1, 128]");
+    if (B < 1) return set_err(WF_ERR_INVALID, "num_envs must be >= 1");
+    if (cfg->table_len < 2 || cfg->table_len > WF_TABLE_MAX) return set_err(WF_ERR_INVALID, "bad table_len");
+    if (cfg->wind_veer != 0.0) return set_err(WF_ERR_INVALID, "wind_veer != 0 is not supported (case.yaml:39 uses 0)");
+    if (!(cfg->yaw_lo < cfg->yaw_hi)) return set_err(WF_ERR_INVALID, "yaw bounds: need low < high (mdp.py:196)");
+    if (cfg->precision != WF_PREC_F64 && cfg->precision != WF_PREC_F32) return set_err(WF_ERR_INVALID, "bad precision");
+    if (cfg->kernel == WF_KERNEL_FAST && cfg->precision != WF_PREC_F32)
+        return set_err(WF_ERR_INVALID, "WF_KERNEL_FAST requires WF_PREC_F32");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(WF_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err(WF_ERR_INVALID, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+
+    WfHandle_t* h = new WfHandle_t();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    h->es = cfg->precision == WF_PREC_F64 ? 8 : 4;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { delete h; return set_err(WF_ERR_CUDA, cudaGetErrorString(e)); }
+    h->sm_count = prop.multiProcessorCount;
+    h->sm_clock_khz = prop.clockRate;
+
+    WfModel& m = h->model;
+    memset(&m, 0, sizeof(m));
+    m.T = T; m.B = B;
+    m.max_iter = cfg->max_iter; m.continuous = cfg->continuous_control; m.multi_agent = cfg->multi_agent;
+    m.shaper = cfg->reward_shaper; m.table_len = cfg->table_len;
+    m.yaw_lo_f = (float)cfg->yaw_lo; m.yaw_hi_f = (float)cfg->yaw_hi; m.yaw_step_f = (float)cfg->yaw_step;
+    m.rate_f = (float)cfg->actuator_rate; m.dt_f = (float)cfg->dt;
+    m.load_coef = cfg->load_coef; m.shaper_reference = cfg->shaper_reference;
+    m.rho = cfg->air_density; m.ref_rho = cfg->ref_density_cp_ct; m.shear = cfg->wind_shear;
+    m.D = cfg->rotor_diameter; m.HH = cfg->hub_height; m.TSR = cfg->tsr; m.pP = cfg->pP;
+    m.alpha = cfg->alpha; m.beta = cfg->beta; m.ka = cfg->ka; m.kb = cfg->kb; m.ad = cfg->ad; m.bd = cfg->bd;
+    m.dm = cfg->dm;
+    m.ch_const = cfg->ch_constant; m.ch_ai = cfg->ch_ai; m.ch_init = cfg->ch_initial; m.ch_down = cfg->ch_downstream;
+    m.e3_112 = 3 * exp(1.0 / 12.0); m.e3_13 = 3 * exp(1.0 / 3.0);
+    double xmin = lx[0], xmax = lx[0], ymin = ly[0], ymax = ly[0];
+    for (int t = 1; t < T; ++t) {
+        xmin = fmin(xmin, lx[t]); xmax = fmax(xmax, lx[t]);
+        ymin = fmin(ymin, ly[t]); ymax = fmax(ymax, ly[t]);
+    }
+    m.xc = (xmin + xmax) / 2; m.yc = (ymin + ymax) / 2;
+
+    int rc = WF_OK;
+    auto fail = [&](int r) { wf_destroy(h); return r; };
+    double *d_ws, *d_ct, *d_pw, *d_lx, *d_ly;
+    if ((rc = dev_alloc(h, &d_ws, cfg->table_len))) return fail(rc);
+    if ((rc = dev_alloc(h, &d_ct, cfg->table_len))) return fail(rc);
+    if ((rc = dev_alloc(h, &d_pw, cfg->table_len))) return fail(rc);
+    if ((rc = dev_alloc(h, &d_lx, T))) return fail(rc);
+    if ((rc = dev_alloc(h, &d_ly, T))) return fail(rc);
+    {
+        std::vector<double> pw(cfg->table_len);
+        const double area = 3.141592653589793 * pow(cfg->rotor_diameter / 2.0, 2.0);
+        for (int i = 0; i < cfg->table_len; ++i)  // FLORIS Turbine.__attrs_post_init__: power / density at the nodes
+            pw[i] = 0.5 * area * cfg->table_cp[i] * cfg->generator_efficiency * pow(cfg->table_ws[i], 3.0);
+        cudaMemcpy(d_ws, cfg->table_ws, sizeof(double) * cfg->table_len, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_ct, cfg->table_ct, sizeof(double) * cfg->table_len, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_pw, pw.data(), sizeof(double) * cfg->table_len, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_lx, lx, sizeof(double) * T, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_ly, ly, sizeof(double) * T, cudaMemcpyHostToDevice);
+    }
+    m.tab_ws = d_ws; m.tab_ct = d_ct; m.tab_pw = d_pw; m.layout_x = d_lx; m.layout_y = d_ly;
+
+    WfState& s = h->st;
+    const size_t BT = (size_t)B * T;
+    if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
+        (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
+        (rc = dev_alloc(h, &s.xi, BT)) || (rc = dev_alloc(h, &s.yi, BT)) || (rc = dev_alloc(h, &s.order, BT)) ||
+        (rc = dev_alloc(h, &s.cs, (size_t)2 * B)) || (rc = dev_alloc(h, &h->d_mask, (size_t)B)) ||
+        (rc = dev_alloc(h, &h->d_rws, (size_t)B)) || (rc = dev_alloc(h, &h->d_rwd, (size_t)B)) ||
+        (rc = dev_alloc(h, &h->d_rcs, (size_t)2 * B)))
+        return fail(rc);
+    if (cudaMallocHost((void**)&h->h_mask, B) != cudaSuccess || cudaMallocHost((void**)&h->h_rws, sizeof(double) * B) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_rwd, sizeof(double) * B) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_rcs, sizeof(double) * 2 * B) != cudaSuccess)
+        return fail(set_err(WF_ERR_NOMEM, "cudaMallocHost failed"));
+    if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(set_err(WF_ERR_CUDA, "cudaStreamCreate failed"));
+
+    // initial condition: wind (8, 270) as in FlorisCase.simul_params (data_cases.py:99-100), ambient TI from the config
+    {
+        std::vector<double> ws(B, 8.0), wd(B, 270.0), ti(B, cfg->turbulence_intensity);
+        cudaMemcpy(h->d_rws, ws.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_rwd, wd.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s.ti_amb, ti.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+        cudaError_t e1 = wf_launch_reset_state(m, s, nullptr, h->d_rws, h->d_rwd, 0);
+        cudaError_t e2 = wf_launch_geometry(m, s, nullptr, nullptr, 0);
+        h->launches += 2;
+        cudaError_t e3 = cudaDeviceSynchronize();
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+            return fail(set_err(WF_ERR_CUDA, std::string("init kernels failed: ") +
+                                                 cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))));
+    }
+    *out = h;
+    return WF_OK;
+}
+
+static WfOutPtrs to_ptrs(const WfStepOut* o) {
+    WfOutPtrs p = {};
+    if (o) {
+        p.yaw = o->yaw; p.wind_speed = o->wind_speed; p.wind_direction = o->wind_direction; p.power = o->power;
+        p.load = o->load; p.reward = o->reward; p.freewind = o->freewind; p.truncated = o->truncated;
+    }
+    return p;
+}
+
+static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float* d_action, const double* d_yaw,
+                       const WfOutPtrs& out, cudaStream_t st) {
+    cudaError_t e;
+    if (h->cfg.kernel == WF_KERNEL_FAST)
+        e = wf_launch_step_fast(mode, h->model, h->st, d_mask, d_action, d_yaw, out, h->sm_count, st);
+    else
+        e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, st);
+    h->launches += 1;
+    if (e != cudaSuccess) return set_err(WF_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
+    return WF_OK;
+}
+
+int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, int32_t warmup,
+                    const WfStepOut* out, void* stream) {
+    if (!h || !d_ws || !d_wd) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(wf_launch_reset_state(h->model, h->st, d_mask, d_ws, d_wd, st));
+    CUDA_TRY(wf_launch_geometry(h->model, h->st, d_mask, nullptr, st));
+    h->launches += 2;
+    for (int k = 0; k < warmup; ++k) TRY(launch_step(h, WF_MODE_WARMUP, d_mask, nullptr, nullptr, to_ptrs(out), st));
+    return WF_OK;
+}
+
+int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const double* wd, const double* hc,
+             const double* hs, int32_t warmup, const WfStepOut* out, void* stream) {
+    if (!h || !ws || !wd) return set_err(WF_ERR_INVALID, "NULL argument");
+    if ((hc == nullptr) != (hs == nullptr)) return set_err(WF_ERR_INVALID, "h_cos and h_sin must be given together");
+    const int B = h->model.B;
+    if (n < 0 || n > B) return set_err(WF_ERR_INVALID, "bad n");
+    if (!ids && n != B) return set_err(WF_ERR_INVALID, "h_env_ids == NULL requires n == num_envs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaStreamSynchronize(st));  // the pinned staging below may still be in flight from a previous reset
+    memset(h->h_mask, 0, B);
+    for (int k = 0; k < n; ++k) {
+        const int b = ids ? ids[k] : k;
+        if (b < 0 || b >= B) return set_err(WF_ERR_INVALID, "env id out of range");
+        h->h_mask[b] = 1;
+        h->h_rws[b] = ws[k];
+        h->h_rwd[b] = wd[k];
+        if (hc) { h->h_rcs[2 * b] = hc[k]; h->h_rcs[2 * b + 1] = hs[k]; }
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_mask, h->h_mask, B, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_rws, h->h_rws, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_rwd, h->h_rwd, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    if (hc) CUDA_TRY(cudaMemcpyAsync(h->d_rcs, h->h_rcs, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(wf_launch_reset_state(h->model, h->st, h->d_mask, h->d_rws, h->d_rwd, st));
+    CUDA_TRY(wf_launch_geometry(h->model, h->st, h->d_mask, hc ? h->d_rcs : nullptr, st));
+    h->launches += 2;
+    for (int k = 0; k < warmup; ++k)
+        TRY(launch_step(h, WF_MODE_WARMUP, h->d_mask, nullptr, nullptr, to_ptrs(out), st));
+    return WF_OK;
+}
+
+int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream) {
+    if (!h || !d_action) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_step(h, WF_MODE_ENV, nullptr, d_action, nullptr, to_ptrs(out), (cudaStream_t)stream);
+}
+
+int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, void* stream) {
+    if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_step(h, WF_MODE_INTERFACE, nullptr, nullptr, d_yaw, to_ptrs(out), (cudaStream_t)stream);
+}
+
+int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_t* h2d, uint64_t* d2h) {
+    if (!h || !h_action || !ho) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t B = h->model.B, T = h->model.T, BT = B * T, es = h->es;
+    if (!h->d_action) {
+        TRY(dev_alloc(h, &h->d_action, BT));
+        char* p;
+        TRY(dev_alloc(h, &p, BT * es)); h->d_out.yaw = p;
+        TRY(dev_alloc(h, &p, BT * es)); h->d_out.wind_speed = p;
+        TRY(dev_alloc(h, &p, BT * es)); h->d_out.wind_direction = p;
+        TRY(dev_alloc(h, &p, BT * es)); h->d_out.power = p;
+        TRY(dev_alloc(h, &p, 4 * BT * es)); h->d_out.load = p;
+        TRY(dev_alloc(h, &p, B * es)); h->d_out.reward = p;
+        TRY(dev_alloc(h, &p, 2 * B * es)); h->d_out.freewind = p;
+        TRY(dev_alloc(h, &h->d_out.truncated, B));
+    }
+    cudaStream_t st = h->host_stream;
+    uint64_t up = 0, down = 0;
+    CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, sizeof(float) * BT, cudaMemcpyHostToDevice, st));
+    up += sizeof(float) * BT;
+    WfOutPtrs o = {};
+    if (ho->yaw) o.yaw = h->d_out.yaw;
+    if (ho->wind_speed) o.wind_speed = h->d_out.wind_speed;
+    if (ho->wind_direction) o.wind_direction = h->d_out.wind_direction;
+    if (ho->power) o.power = h->d_out.power;
+    if (ho->load) o.load = h->d_out.load;
+    if (ho->reward) o.reward = h->d_out.reward;
+    if (ho->freewind) o.freewind = h->d_out.freewind;
+    if (ho->truncated) o.truncated = h->d_out.truncated;
+    TRY(launch_step(h, WF_MODE_ENV, nullptr, h->d_action, nullptr, o, st));
+#define D2H(field, bytes)                                                                              \
+    if (ho->field) {                                                                                   \
+        CUDA_TRY(cudaMemcpyAsync(ho->field, h->d_out.field, (bytes), cudaMemcpyDeviceToHost, st));      \
+        down += (bytes);                                                                               \
+    }
+    D2H(yaw, BT * es) D2H(wind_speed, BT * es) D2H(wind_direction, BT * es) D2H(power, BT * es) D2H(load, 4 * BT * es)
+    D2H(reward, B * es) D2H(freewind, 2 * B * es) D2H(truncated, B)
+#undef D2H
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h2d) *h2d = up;
+    if (d2h) *d2h = down;
+    return WF_OK;
+}
+
+int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, void* stream) {
+    if (!h || !d_ws || !d_wd) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = h->model.B;
+    if (d_mask) return set_err(WF_ERR_INVALID, "masked wf_update_wind is not implemented yet");
+    CUDA_TRY(cudaMemcpyAsync(h->st.ws, d_ws, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->st.wd, d_wd, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(wf_launch_geometry(h->model, h->st, nullptr, nullptr, st));
+    h->launches += 1;
+    return WF_OK;
+}
+
+int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream) {
+    if (!h || !d_ti) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->st.ti_amb, d_ti, sizeof(double) * h->model.B, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return WF_OK;
+}
+
+static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
+    const size_t B = h->model.B, BT = B * h->model.T;
+    const WfState& s = h->st;
+    struct { const char* n; void* p; size_t b; } tab[] = {
+        {"yaw", s.yaw, BT * 8}, {"acc", s.acc, BT * 4}, {"acc_prev", s.acc_prev, BT * 4},
+        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
+        {"ws_norm", s.ws_norm, B * 8}, {"shaper_ref", s.shaper_ref, B * 8}, {"ti_ambient", s.ti_amb, B * 8},
+        {"order", s.order, BT * 4}, {"xs", s.xs, BT * 8}, {"ys", s.ys, BT * 8}, {"xi", s.xi, BT * 8},
+        {"yi", s.yi, BT * 8}, {"cs", s.cs, B * 16}};
+    for (auto& e : tab)
+        if (!strcmp(e.n, name)) { *p = e.p; *bytes = e.b; return WF_OK; }
+    return set_err(WF_ERR_INVALID, std::string("unknown state array '") + name + "'");
+}
+
+int wf_get_state(WfHandle h, const char* name, void* dst, size_t bytes) {
+    if (!h || !name || !dst) return set_err(WF_ERR_INVALID, "NULL argument");
+    void* p; size_t b;
+    TRY(find_state(h, name, &p, &b));
+    if (b != bytes) return set_err(WF_ERR_INVALID, "size mismatch for state array");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(dst, p, b, cudaMemcpyDeviceToHost));
+    return WF_OK;
+}
+
+int wf_set_state(WfHandle h, const char* name, const void* src, size_t bytes) {
+    if (!h || !name || !src) return set_err(WF_ERR_INVALID, "NULL argument");
+    void* p; size_t b;
+    TRY(find_state(h, name, &p, &b));
+    if (b != bytes) return set_err(WF_ERR_INVALID, "size mismatch for state array");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(p, src, b, cudaMemcpyHostToDevice));
+    return WF_OK;
+}
+
+int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t* ctas_per_sm, int32_t* regs,
+                   int32_t* threads, int32_t* smem) {
+    if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaFuncAttributes attr;
+    int ctas = 0, thr = (h->model.T + 31) / 32 * 32, sm = 0;
+    if (h->cfg.kernel == WF_KERNEL_FAST) {
+        CUDA_TRY(wf_step_fast_attributes(h->model, &attr, &ctas, &thr, &sm));
+    } else {
+        CUDA_TRY(wf_step_basic_attributes(h->cfg.precision, &attr, &ctas, thr));
+        sm = (int)attr.sharedSizeBytes;
+    }
+    if (sm_count) *sm_count = h->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = h->sm_clock_khz;
+    if (ctas_per_sm) *ctas_per_sm = ctas;
+    if (regs) *regs = attr.numRegs;
+    if (threads) *threads = thr;
+    if (smem) *smem = sm;
+    return WF_OK;
+}
+
+uint64_t wf_launch_count(WfHandle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

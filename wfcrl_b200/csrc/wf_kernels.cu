@@ -1,0 +1,687 @@
+// Hand-written sm_100a kernels for the FLORIS GCH steady-state solve + WFCRL env step (basic variant).
+//
+// One CTA per environment, one thread per turbine (in downstream-sorted order).  Each thread keeps the 3x3 rotor
+// grid state of ITS turbine (wake deficit, v, w, turbulence intensity) in registers; the sequential solver loop
+// over sources i = 0..T-1 broadcasts the source turbine's parameters through a double-buffered shared-memory record
+// with ONE __syncthreads per source.  The same template instantiates the FP64 bit-check kernel and a plain FP32
+// kernel (x-direction masks always come from FP64 differences).
+//
+// Algorithm: SURVEY.md Appendix A (restatement of FLORIS 3.5 as configured by
+// wfcrl/simulators/floris/inputs/template/case.yaml) -- reference call sites wfcrl/interface.py:557-586, 622-648;
+// env semantics wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py.
+#include "wf_device.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kNumEps = 0.001;  // floris BaseModel.NUM_EPS
+
+// ---------------------------------------------------------------------------------------------------------------
+// math traits
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R> struct M;
+template <> struct M<double> {
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double cbrt(double x) { return ::cbrt(x); }
+    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double tan(double x) { return ::tan(x); }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double hypot(double a, double b) { return ::hypot(a, b); }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
+};
+template <> struct M<float> {
+    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float cbrt(float x) { return cbrtf(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return __powf(x, y); }
+    static __device__ __forceinline__ float asin(float x) { return asinf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float tan(float x) { return tanf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float hypot(float a, float b) { return sqrtf(fmaf(a, a, b * b)); }
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+};
+
+// numpy's reduction order over the 9 contiguous grid values (pairwise over the first 8, then the 9th)
+template <typename R> __device__ __forceinline__ R sum9(const R* p) {
+    return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
+}
+template <typename R> __device__ __forceinline__ R mean9(const R* p) { return M<R>::div(sum9(p), R(9)); }
+
+// python float % for a positive modulus
+__device__ __forceinline__ double fmod_py(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && r < 0.0) r += m;
+    return r;
+}
+
+// np.interp + scipy interp1d fill values on the turbine table (table lives in global memory, L1-resident)
+__device__ __forceinline__ double interp_table(double x, const double* __restrict__ xp, const double* __restrict__ fp,
+                                               int n, double left, double right) {
+    if (x < xp[0]) return left;
+    if (x > xp[n - 1]) return right;
+    if (x == xp[n - 1]) return fp[n - 1];
+    int lo = 0, hi = n - 1;  // invariant xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    double x0 = xp[lo], f0 = fp[lo];
+    if (x == x0) return f0;
+    double slope = (fp[lo + 1] - f0) / (xp[lo + 1] - x0);
+    return slope * (x - x0) + f0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory layouts
+// ---------------------------------------------------------------------------------------------------------------
+// Per-env constants computed once per step by thread 0.
+template <typename R> struct EnvConst {
+    R U0[3], nu4[3];       // initial velocity per vertical index k; 4*nu/Uinf per k (transverse-velocity decay)
+    R zq[6][3];            // Z_k + c_v + NUM_EPS for the 6 vortices (top, bottom, top-mirror, bottom-mirror, core, core-mirror)
+    R Uinf, vel_top, vel_bot, eps2, inv_eps2, I0;
+    double wd, ws;
+};
+
+// Per-source broadcast record (double buffered).
+template <typename R> struct SrcRec {
+    double x_i, y_i;       // FP64: every x-mask is decided on the FP64 difference X - x_i
+    R ct, a, Gt, Gb, Gwr;  // thrust coeff (incl. cos yaw), axial induction, vortex circulations
+    R cgv;                 // cosd(-yaw_i)
+    R sM0, tan_th, Kc;     // deflection scalars
+    R sy0d, sz0d;          // sigma_y0, sigma_z0 of the deflection model (effective yaw)
+    R sy0v, sz0v;          // sigma_y0, sigma_z0 of the velocity model
+    R near_s;              // 0.501 * D * sqrt(ct / 2)
+    R ctc;                 // ct * cosd(-yaw_i) * D^2 / 8
+    R watK;                // constant * a^ai * I0^initial
+    R x0d[WF_NP], kyd[WF_NP];  // near-wake length (relative to x_i) and expansion rate from the PRE-update TI
+    R x0v[WF_NP], kyv[WF_NP];  // same from the POST-update TI (velocity model)
+};
+
+// The six vortices of calculate_transverse_velocity in FLORIS' summation order V1..V6:
+//   V1 top (+Gt), V2 bottom (+Gb), V3 top ground mirror (-Gt), V4 bottom ground mirror (-Gb),
+//   V5 wake rotation (+Gwr), V6 wake rotation ground mirror (-Gwr).
+template <typename R>
+__device__ __forceinline__ void transverse(const EnvConst<R>& ec, R Gt, R Gb, R Gwr, R yL, int k, R decay, R* V, R* W) {
+    const R two_pi = R(2.0 * kPi);
+    const R yy = yL * yL;
+    R Vs = R(0), Ws = R(0);
+    const R gam[6] = {Gt, Gb, -Gt, -Gb, Gwr, -Gwr};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const R zz = ec.zq[q][k];
+        const R r = yy + zz * zz;
+        const R core = R(1) - M<R>::exp(-r * ec.inv_eps2);
+        const R f = M<R>::div(core * decay, two_pi * r);
+        Vs += (gam[q] * zz) * f;
+        Ws += (-gam[q] * yL) * f;
+    }
+    *V = Vs;
+    *W = Ws;
+}
+
+// lateral offset (Y - y_i) of grid column j of a target at rotated y `ys_t` from the source centre y_i
+template <typename R> struct Lat {
+    // returns (Y - y_i) exactly like the reference: Y = fl(ys + off_j) in FP64
+    static __device__ __forceinline__ R get(double ys_t, double y_i, double offj);
+};
+template <> struct Lat<double> {
+    static __device__ __forceinline__ double get(double ys_t, double y_i, double offj) {
+        return __dsub_rn(__dadd_rn(ys_t, offj), y_i);
+    }
+};
+template <> struct Lat<float> {
+    static __device__ __forceinline__ float get(double ys_t, double y_i, double offj) {
+        return (float)(ys_t - y_i) + (float)offj;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// geometry kernel: rotate, stable sort, per-turbine means.  One CTA per env, one thread per turbine.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WF_MAX_TURBINES_K)
+wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
+                   const double* __restrict__ cs_override) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    const int t = threadIdx.x;
+    __shared__ double xr[WF_MAX_TURBINES_K], yr[WF_MAX_TURBINES_K];
+    __shared__ double cs[2];
+    if (t == 0) {
+        double c, sn;
+        if (cs_override) {
+            c = cs_override[2 * b];
+            sn = cs_override[2 * b + 1];
+        } else {
+            const double wd = s.wd[b];
+            const double dev = fmod_py(fmod_py(wd - 270.0, 360.0) + 360.0, 360.0);
+            const double rad = dev * (kPi / 180.0);
+            c = cos(rad);
+            sn = sin(rad);
+        }
+        cs[0] = c;
+        cs[1] = sn;
+        s.cs[2 * b] = c;
+        s.cs[2 * b + 1] = sn;
+    }
+    __syncthreads();
+    if (t < T) {
+        const double xo = __dsub_rn(m.layout_x[t], m.xc), yo = __dsub_rn(m.layout_y[t], m.yc);
+        // every product / sum separately rounded: no FMA contraction
+        xr[t] = __dadd_rn(__dsub_rn(__dmul_rn(xo, cs[0]), __dmul_rn(yo, cs[1])), m.xc);
+        yr[t] = __dadd_rn(__dadd_rn(__dmul_rn(xo, cs[1]), __dmul_rn(yo, cs[0])), m.yc);
+    }
+    __syncthreads();
+    if (t < T) {
+        const double x = xr[t], y = yr[t];
+        int rank = 0;
+        for (int q = 0; q < T; ++q) {
+            const double xq = xr[q];
+            rank += (xq < x) || (xq == x && q < t);  // stable ascending
+        }
+        const size_t o = (size_t)b * T + rank;
+        s.xs[o] = x;
+        s.ys[o] = y;
+        s.order[o] = t;
+        s.xi[o] = __ddiv_rn(__dadd_rn(__dmul_rn(8.0, x), x), 9.0);
+        const double off = 0.5 * m.D / 2;  // disc_area_radius: grid offsets -off, 0, +off
+        const double ya = __dadd_rn(y, -off), yb = __dadd_rn(y, 0.0), yc = __dadd_rn(y, off);
+        // flattened grid values p = 3j + k: ya ya ya yb yb yb yc yc yc ; numpy order ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) + p8
+        const double s03 = __dadd_rn(__dadd_rn(ya, ya), __dadd_rn(ya, yb));
+        const double s47 = __dadd_rn(__dadd_rn(yb, yb), __dadd_rn(yc, yc));
+        s.yi[o] = __ddiv_rn(__dadd_rn(__dadd_rn(s03, s47), yc), 9.0);
+    }
+}
+
+// reset per-env scalars/accumulators for masked envs
+__global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
+                                      const double* __restrict__ ws, const double* __restrict__ wd) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const size_t o = (size_t)b * T + t;
+        s.yaw[o] = 0.0;
+        s.acc[o] = 0.f;
+        s.acc_prev[o] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        const double w = ws[b];
+        s.ws[b] = w;
+        s.wd[b] = fmod_py(wd[b], 360.0);  // interface.py:664
+        s.ws_norm[b] = fmin(fmax(w, 3.0), 28.0);  // start_state is clipped to the observation space (mdp.py:266)
+        s.num_iter[b] = 0;
+        s.num_moves[b] = 0;
+        s.shaper_ref[b] = m.shaper_reference;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// step kernel (basic variant)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(WF_MAX_TURBINES_K)
+wf_step_basic_kernel(const int mode, const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
+                     const float* __restrict__ action, const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    const int t = threadIdx.x;
+    const size_t row = (size_t)b * T;
+
+    __shared__ EnvConst<R> ec;
+    __shared__ SrcRec<R> rec[2];
+    __shared__ double sh_yaw[WF_MAX_TURBINES_K];   // new yaw in ORIGINAL order
+    __shared__ double sh_red0[WF_MAX_TURBINES_K];  // reward reduction scratch (original order)
+    __shared__ double sh_red1[WF_MAX_TURBINES_K];
+
+    const R D = (R)m.D, HH = (R)m.HH;
+    const double offd = 0.5 * m.D / 2;
+
+    // ---- env prologue: thread t handles ORIGINAL turbine t (mdp.py:291-319, simple_env.py:64-72) ----------------
+    int nm = 0;
+    if (mode == WF_MODE_ENV) nm = s.num_moves[b] + 1;
+    if (t < T) {
+        double ynew;
+        if (mode == WF_MODE_ENV) {
+            float a = action[row + t];
+            const float acc = s.acc[row + t];
+            const float acc_c = (m.multi_agent && t != T - 1) ? s.acc_prev[row + t] : acc;
+            // actuating_frac = acc / rate / num_moves / dt, evaluated in float32 like numpy does
+            const float frac = __fdiv_rn(__fdiv_rn(__fdiv_rn(acc_c, m.rate_f), (float)nm), m.dt_f);
+            if (frac >= 0.1f) a = 0.0f;
+            if (m.continuous) a = fminf(fmaxf(a, -m.yaw_step_f), m.yaw_step_f);
+            else a = __fmul_rn(__fsub_rn(a, 1.0f), m.yaw_step_f);
+            const float y0 = fminf(fmaxf((float)s.yaw[row + t], m.yaw_lo_f), m.yaw_hi_f);
+            const float y1 = fminf(fmaxf(__fadd_rn(y0, a), m.yaw_lo_f), m.yaw_hi_f);
+            s.acc_prev[row + t] = acc;
+            s.acc[row + t] = __fadd_rn(acc, fabsf(a));
+            ynew = (double)y1;
+            s.yaw[row + t] = ynew;
+        } else if (mode == WF_MODE_INTERFACE && yaw_cmd) {
+            ynew = yaw_cmd[row + t];
+            s.yaw[row + t] = ynew;
+        } else {
+            ynew = s.yaw[row + t];
+        }
+        sh_yaw[t] = ynew;
+    }
+    if (t == 0) {
+        const double ws = s.ws[b], wd = s.wd[b];
+        ec.ws = ws;
+        ec.wd = wd;
+        const double I0 = s.ti_amb[b];
+        ec.I0 = (R)I0;
+        const double eps = 0.2 * m.D;
+        ec.eps2 = (R)(eps * eps);
+        ec.inv_eps2 = (R)(1.0 / (eps * eps));
+        double U0[3], usum = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const double Z = m.HH + (k - 1) * offd;
+            U0[k] = ws * pow(Z / m.HH, m.shear);
+            usum += U0[k];
+        }
+        const double Uinf = usum / 3.0;
+        ec.Uinf = (R)Uinf;
+        for (int k = 0; k < 3; ++k) {
+            const double Z = m.HH + (k - 1) * offd;
+            const double dU = ws * (m.shear * pow(1.0 / m.HH, m.shear) * pow(Z, m.shear - 1.0));
+            const double lmda = m.D / 8, kappa = 0.41;
+            const double lm = kappa * Z / (1 + kappa * Z / lmda);
+            const double nu = lm * lm * fabs(dU);
+            ec.U0[k] = (R)U0[k];
+            ec.nu4[k] = (R)(4 * nu / Uinf);
+            const double zc[6] = {-(m.HH + m.D / 2), -(m.HH - m.D / 2), (m.HH + m.D / 2), (m.HH - m.D / 2), -m.HH, m.HH};
+            for (int q = 0; q < 6; ++q) ec.zq[q][k] = (R)((Z + zc[q]) + kNumEps);
+        }
+        ec.vel_top = (R)pow((m.HH + m.D / 2) / m.HH, m.shear);
+        ec.vel_bot = (R)pow((m.HH - m.D / 2) / m.HH, m.shear);
+    }
+    __syncthreads();
+
+    // ---- per-thread state: turbine at sorted position t ----------------------------------------------------------
+    R wake[WF_NP], v[WF_NP], w[WF_NP], ti[WF_NP];
+    double X = 0.0, Ys = 0.0, yaw_t = 0.0;
+    int orig = 0;
+    if (t < T) {
+        X = s.xs[row + t];
+        Ys = s.ys[row + t];
+        orig = s.order[row + t];
+        yaw_t = sh_yaw[orig];
+    }
+#pragma unroll
+    for (int p = 0; p < WF_NP; ++p) { wake[p] = R(0); v[p] = R(0); w[p] = R(0); ti[p] = ec.I0; }
+    const R I0 = ec.I0;
+    const R inv_D = M<R>::div(R(1), D);
+
+    // ---- sequential solver over sources ---------------------------------------------------------------------------
+    for (int i = 0; i < T; ++i) {
+        SrcRec<R>& rc = rec[i & 1];
+        if (t == i) {
+            // ===== source prologue (A.4, A.5, source part of A.6-A.8) =====
+            const double x_i = s.xi[row + i], y_i = s.yi[row + i];
+            R u[WF_NP], c3[WF_NP];
+#pragma unroll
+            for (int p = 0; p < WF_NP; ++p) { u[p] = ec.U0[p % 3] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
+            const R avg = M<R>::cbrt(mean9(c3));
+            double ctd = interp_table((double)avg, m.tab_ws, m.tab_ct, m.table_len, 0.0001, 0.9999);
+            ctd = fmin(fmax(ctd, 0.0001), 0.9999);
+            R sy, cy;
+            M<R>::sincos((R)(yaw_t * (kPi / 180.0)), &sy, &cy);
+            const R ct = (R)ctd * cy;
+            const R a = M<R>::div(R(0.5), cy) * (R(1) - M<R>::sqrt(R(1) - ct * cy));
+            const R G_top0 = (R)(kPi / 8) * D * ec.vel_top * ec.Uinf * ct;
+            const R G_bot0 = (R)(kPi / 8) * D * ec.vel_bot * ec.Uinf * ct;
+            const R Gwr = M<R>::div((R)(0.25 * 2 * kPi) * D * (a - a * a) * avg, (R)m.TSR);
+            const R Gt = sy * cy * G_top0, Gb = -(sy * cy * G_bot0);
+
+            // A.5 secondary steering on the source's own grid: top (+G_top0), bottom (-G_bot0), wake rotation
+            R vt[WF_NP], vb[WF_NP], vc[WF_NP];
+#pragma unroll
+            for (int p = 0; p < WF_NP; ++p) {
+                const int j = p / 3, k = p % 3;
+                const R yL = Lat<R>::get(Ys, y_i, (j - 1) * offd) + (R)kNumEps;
+                const R yy = yL * yL;
+                const R two_pi = R(2.0 * kPi);
+                R zz = ec.zq[0][k], r = yy + zz * zz;
+                vt[p] = M<R>::div(G_top0 * zz, two_pi * r) * (R(1) - M<R>::exp(-r * ec.inv_eps2));
+                zz = ec.zq[1][k]; r = yy + zz * zz;
+                vb[p] = M<R>::div(-G_bot0 * zz, two_pi * r) * (R(1) - M<R>::exp(-r * ec.inv_eps2));
+                zz = ec.zq[4][k]; r = yy + zz * zz;
+                vc[p] = M<R>::div(Gwr * zz, two_pi * r) * (R(1) - M<R>::exp(-r * ec.inv_eps2));
+            }
+            R val = M<R>::div(R(2) * (mean9(v) - mean9(vc)), mean9(vt) + mean9(vb));
+            val = M<R>::min(M<R>::max(val, R(-1)), R(1));
+            const R eff_yaw = (R)yaw_t + (R)(180.0 / kPi) * (R(0.5) * M<R>::asin(val));
+
+            // A.6 deflection scalars (opposite sign convention)
+            const R g = -eff_yaw;
+            R sg, cg;
+            M<R>::sincos(g * (R)(kPi / 180.0), &sg, &cg);
+            const R sq1ct = M<R>::sqrt(R(1) - ct);            // sqrt(1 - ct)
+            const R sq1ctcg = M<R>::sqrt(R(1) - ct * cg);     // sqrt(1 - ct cos(g))
+            {
+                // uR/(U0 + u0), C0, M0, E0 do not depend on the grid point (U0 cancels)
+                const R uR_over = M<R>::div(ct * cg, R(2) * (R(1) - sq1ctcg));
+                const R sz0 = D * R(0.5) * M<R>::sqrt(M<R>::div(uR_over, R(1) + sq1ct));
+                const R sy0 = sz0 * cg;  // cosd(veer) = 1
+                const R C0 = R(1) - sq1ct;
+                const R M0 = C0 * (R(2) - C0);
+                const R E0 = C0 * C0 - (R)m.e3_112 * C0 + (R)m.e3_13;  // 3 e^(1/12), 3 e^(1/3)
+                R th = (R)m.dm * M<R>::div(R(0.3) * (g * (R)(kPi / 180.0)), cg);
+                th = th * (R(1) - sq1ctcg);
+                rc.sM0 = M<R>::sqrt(M0);
+                rc.tan_th = M<R>::tan(th);
+                rc.Kc = M<R>::div(th * E0, R(5.2)) * M<R>::sqrt(M<R>::div(sy0 * sz0, M0));
+                rc.sy0d = sy0;
+                rc.sz0d = sz0;
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) {
+                    rc.x0d[p] = M<R>::div(D * (cg * (R(1) + sq1ctcg)),
+                                          (R)1.4142135623730951 * (R(4) * (R)m.alpha * ti[p] + R(2) * (R)m.beta * (R(1) - sq1ct)));
+                    rc.kyd[p] = (R)m.ka * ti[p] + (R)m.kb;
+                }
+            }
+
+            // own transverse velocities (A.7) -> yaw-added recovery TI update (in place) -> own v, w updated now
+            {
+                const double dxs = X - x_i;
+                R Vp[WF_NP], Wp[WF_NP];
+                if (dxs < 0.0) {
+#pragma unroll
+                    for (int p = 0; p < WF_NP; ++p) { Vp[p] = R(0); Wp[p] = R(0); }
+                } else {
+                    const R dx = (R)dxs;
+#pragma unroll
+                    for (int p = 0; p < WF_NP; ++p) {
+                        const int j = p / 3, k = p % 3;
+                        const R yL = Lat<R>::get(Ys, y_i, (j - 1) * offd) + (R)kNumEps;
+                        const R decay = M<R>::div(ec.eps2, ec.nu4[k] * dx + ec.eps2);
+                        transverse<R>(ec, Gt, Gb, Gwr, yL, k, decay, &Vp[p], &Wp[p]);
+                        Wp[p] = M<R>::max(Wp[p], R(0));
+                    }
+                }
+                const R I = ti[0];
+                const R aI = avg * I;
+                const R kk = M<R>::div(aI * aI, (R)(2.0 / 3.0));
+                const R u_term = M<R>::sqrt(R(2) * kk);
+                R tv[WF_NP], tw[WF_NP];
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) { tv[p] = v[p] + Vp[p]; tw[p] = w[p] + Wp[p]; }
+                const R v_term = mean9(tv), w_term = mean9(tw);
+                const R k_total = R(0.5) * (u_term * u_term + v_term * v_term + w_term * w_term);
+                const R I_total = M<R>::div(M<R>::sqrt((R)(2.0 / 3.0) * k_total), avg);
+                const R I_mix = I_total - I;
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) { ti[p] = ti[p] + R(2) * I_mix; v[p] = tv[p]; w[p] = tw[p]; }
+            }
+
+            // A.8 velocity-model scalars with the UPDATED TI (uses yaw_i, opposite sign: cos(-yaw) = cy)
+            {
+                const R cgv = cy;
+                const R uR_over = M<R>::div(ct, R(2) * (R(1) - sq1ct));
+                const R sz0 = D * R(0.5) * M<R>::sqrt(M<R>::div(uR_over, R(1) + sq1ct));
+                rc.sz0v = sz0;
+                rc.sy0v = sz0 * cgv;
+                rc.cgv = cgv;
+                rc.near_s = R(0.501) * D * M<R>::sqrt(ct * R(0.5));
+                rc.ctc = ct * cgv * D * D * R(0.125);
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) {
+                    rc.x0v[p] = M<R>::div(D * cgv * (R(1) + sq1ct),
+                                          (R)1.4142135623730951 * (R(4) * (R)m.alpha * ti[p] + R(2) * (R)m.beta * (R(1) - sq1ct)));
+                    rc.kyv[p] = (R)m.ka * ti[p] + (R)m.kb;
+                }
+            }
+            rc.x_i = x_i;
+            rc.y_i = y_i;
+            rc.ct = ct;
+            rc.a = a;
+            rc.Gt = Gt;
+            rc.Gb = Gb;
+            rc.Gwr = Gwr;
+            rc.watK = (R)m.ch_const * M<R>::pow(a, (R)m.ch_ai) * M<R>::pow(I0, (R)m.ch_init);
+        }
+        __syncthreads();
+        if (t < T && t != i) {
+            const double dxd = X - rc.x_i;
+            if (dxd >= 0.0) {
+                // ===== target update (A.6-A.8) on the 9 rotor points of turbine t =====
+                const R dx = (R)dxd;
+                const bool gt01 = X > __dadd_rn(rc.x_i, 0.1);   // near-wake mask bump
+                const bool gt0 = X > rc.x_i;
+                const bool le15 = X <= __dadd_rn(15 * m.D, rc.x_i);
+                const R Gt = rc.Gt, Gb = rc.Gb, Gwr = rc.Gwr;
+                R dU[WF_NP];
+                int cnt = 0;
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) {
+                    const int j = p / 3, k = p % 3;
+                    const R dyc = Lat<R>::get(Ys, rc.y_i, (j - 1) * offd);  // Y - y_i
+                    // -- transverse velocities
+                    {
+                        const R decay = M<R>::div(ec.eps2, ec.nu4[k] * dx + ec.eps2);
+                        R Vq, Wq;
+                        transverse<R>(ec, Gt, Gb, Gwr, dyc + (R)kNumEps, k, decay, &Vq, &Wq);
+                        v[p] += Vq;
+                        w[p] += M<R>::max(Wq, R(0));
+                    }
+                    // -- deflection
+                    R defl;
+                    {
+                        const R x0 = rc.x0d[p], ky = rc.kyd[p];
+                        const R delta0 = rc.tan_th * x0;
+                        const R lin = (R)m.ad + (R)m.bd * dx;
+                        if (dx <= x0) {
+                            defl = M<R>::div(dx, x0) * delta0 + lin;
+                        } else {
+                            const R sgy = ky * (dx - x0) + rc.sy0d, sgz = ky * (dx - x0) + rc.sz0d;
+                            const R sq = M<R>::sqrt(M<R>::div(sgy * sgz, rc.sy0d * rc.sz0d));
+                            const R num = (R(1.6) + rc.sM0) * (R(1.6) * sq - rc.sM0);
+                            const R den = (R(1.6) - rc.sM0) * (R(1.6) * sq + rc.sM0);
+                            defl = delta0 + M<R>::div(rc.Kc, ky) * M<R>::log(M<R>::div(num, den)) + lin;
+                        }
+                    }
+                    // -- Gauss deficit
+                    R deficit = R(0);
+                    {
+                        const R x0 = rc.x0v[p];
+                        const bool far = dx >= x0;
+                        const bool near = gt01 && !far;
+                        if (near || far) {
+                            R sgy, sgz;
+                            if (far) {
+                                const R ky = rc.kyv[p];
+                                sgy = ky * (dx - x0) + rc.sy0v;
+                                sgz = ky * (dx - x0) + rc.sz0v;
+                            } else {
+                                const R up = M<R>::div(dx, x0), down = M<R>::div(x0 - dx, x0);
+                                sgy = down * rc.near_s + up * rc.sy0v;
+                                sgz = down * rc.near_s + up * rc.sz0v;
+                            }
+                            const R dy = dyc - defl;
+                            const R dz = (R)((k - 1) * offd);
+                            const R r = M<R>::div(dy * dy, R(2) * sgy * sgy) + M<R>::div(dz * dz, R(2) * sgz * sgz);
+                            R d = R(1) - M<R>::div(rc.ctc, sgy * sgz);
+                            d = M<R>::min(M<R>::max(d, R(0)), R(1));
+                            deficit = (R(1) - M<R>::sqrt(d)) * M<R>::exp(-r);
+                        }
+                    }
+                    dU[p] = deficit * ec.U0[k];
+                    cnt += dU[p] > R(0.05);
+                }
+                // -- Crespo-Hernandez wake-added TI (A.8e): only non-zero when the wake overlaps the rotor
+                R ti_add_base = R(0);
+                if (cnt > 0 && gt0 && le15) {
+                    const R dxp = dx + ((dxd <= 0.1) ? R(1) : R(0));
+                    const R wat = rc.watK * M<R>::pow(dxp * inv_D, (R)m.ch_down);
+                    ti_add_base = ((R)cnt * (R)(1.0 / 9.0)) * wat;
+                }
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) {
+                    const int j = p / 3;
+                    const R dyc = Lat<R>::get(Ys, rc.y_i, (j - 1) * offd);
+                    const R ta = (M<R>::abs(dyc) < R(2) * D) ? ti_add_base : R(0);
+                    ti[p] = M<R>::max(M<R>::sqrt(ta * ta + I0 * I0), ti[p]);
+                    wake[p] = M<R>::hypot(wake[p], dU[p]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: measures (interface.py:565-577, 622-648), power (A.10), reward (simple_env.py:78-85) -----------
+    const bool env = (mode != WF_MODE_INTERFACE);
+    R p_out = R(0), lsum = R(0);
+    if (t < T) {
+        R u[WF_NP], c3[WF_NP], dd[WF_NP];
+#pragma unroll
+        for (int p = 0; p < WF_NP; ++p) { u[p] = ec.U0[p % 3] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
+        const R avg = M<R>::cbrt(mean9(c3));
+        R sy, cy;
+        M<R>::sincos((R)(yaw_t * (kPi / 180.0)), &sy, &cy);
+        const double veff = (double)((R)cbrt(m.rho / m.ref_rho) * avg * M<R>::pow(cy, (R)(m.pP / 3.0)));
+        const double pw = interp_table(veff, m.tab_ws, m.tab_pw, m.table_len, 0.0, 0.0) * m.ref_rho;  // [W]
+#pragma unroll
+        for (int p = 0; p < WF_NP; ++p) dd[p] = (R)ec.wd - (R)(180.0 / kPi) * M<R>::atan2(v[p], u[p]);
+        R wdl = mean9(dd);
+        R wsl = avg;
+        const R ti_m = mean9(ti);
+        R sd[3];
+        {
+            const R* arrs[3] = {u, v, w};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const R mu = mean9(arrs[q]);
+                R d2[WF_NP];
+#pragma unroll
+                for (int p = 0; p < WF_NP; ++p) { const R e = arrs[q][p] - mu; d2[p] = e * e; }
+                sd[q] = M<R>::sqrt(mean9(d2));
+            }
+        }
+        R loads[4] = {ti_m, sd[0], sd[1], sd[2]};
+        if (env) {
+            p_out = (R)(pw / 1e6);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (sizeof(R) == 8) loads[q] = (R)(((double)loads[q] * 1e7) / 1e7);
+                lsum += M<R>::abs(loads[q]);
+            }
+        } else {
+            p_out = (R)pw;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) loads[q] = (R)((double)loads[q] * 1e7);
+        }
+        if (mode == WF_MODE_WARMUP) {  // start state is clipped to the observation space (mdp.py:263-266)
+            wsl = M<R>::min(M<R>::max(wsl, R(3)), R(28));
+            wdl = M<R>::min(M<R>::max(wdl, R(0)), R(360));
+        }
+        const size_t o = row + orig;
+        if (out.yaw) {
+            R yv = (R)yaw_t;
+            if (mode == WF_MODE_WARMUP) yv = M<R>::min(M<R>::max(yv, (R)m.yaw_lo_f), (R)m.yaw_hi_f);
+            ((R*)out.yaw)[o] = yv;
+        }
+        if (out.wind_speed) ((R*)out.wind_speed)[o] = wsl;
+        if (out.wind_direction) ((R*)out.wind_direction)[o] = wdl;
+        if (out.power) ((R*)out.power)[o] = p_out;
+        if (out.load) {
+            R* L = (R*)out.load + 4 * o;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) L[q] = loads[q];
+        }
+        sh_red0[orig] = (double)p_out;
+        sh_red1[orig] = (double)lsum;
+    }
+    __syncthreads();
+    if (t == 0) {
+        const int it = s.num_iter[b] + 1;
+        s.num_iter[b] = it;
+        if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
+        double fw0 = ec.ws, fw1 = ec.wd;
+        if (mode == WF_MODE_WARMUP) {
+            fw0 = fmin(fmax(fw0, 3.0), 28.0);
+            fw1 = fmin(fmax(fw1, 0.0), 360.0);
+        }
+        if (out.freewind) {
+            ((R*)out.freewind)[2 * b] = (R)fw0;
+            ((R*)out.freewind)[2 * b + 1] = (R)fw1;
+        }
+        if (mode == WF_MODE_ENV) {
+            s.num_moves[b] = nm;
+            const double wn = s.ws_norm[b];
+            const double w3 = wn * wn * wn;
+            double sp = 0.0, sl = 0.0;
+            for (int q = 0; q < T; ++q) {
+                sp += sh_red0[q] * 1e3 / w3;
+                sl += sh_red1[q];
+            }
+            double reward = sp / T - m.load_coef * (sl / (4.0 * T));
+            if (m.shaper == 1) {
+                reward = (reward - m.shaper_reference) / m.shaper_reference;
+            } else if (m.shaper == 2) {
+                const double ref = s.shaper_ref[b];
+                const double shaped = (ref == 0.0) ? 0.0 : (reward - ref) / ref;
+                s.shaper_ref[b] = reward;
+                reward = shaped;
+            }
+            if (out.reward) ((R*)out.reward)[b] = (R)reward;
+            s.ws_norm[b] = ec.ws;  // next state's freewind measurement (mdp.py:280)
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+static inline int round_up_warp(int n) { return (n + 31) / 32 * 32; }
+
+cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_cs_override,
+                               cudaStream_t stream) {
+    wf_geometry_kernel<<<m.B, round_up_warp(m.T), 0, stream>>>(m, s, d_mask, d_cs_override);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
+                                  const double* d_wd, cudaStream_t stream) {
+    wf_reset_state_kernel<<<m.B, 32, 0, stream>>>(m, s, d_mask, d_ws, d_wd);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
+                                 const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
+                                 cudaStream_t stream) {
+    const int threads = round_up_warp(m.T);
+    if (precision == 0)
+        wf_step_basic_kernel<double><<<m.B, threads, 0, stream>>>(mode, m, s, d_mask, d_action, d_yaw_cmd, out);
+    else
+        wf_step_basic_kernel<float><<<m.B, threads, 0, stream>>>(mode, m, s, d_mask, d_action, d_yaw_cmd, out);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads) {
+    cudaError_t e;
+    if (precision == 0) {
+        e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<double>);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<double>, threads, 0);
+    }
+    e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<float>);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<float>, threads, 0);
+}
