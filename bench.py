@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path BASELINE.json names: Floris env-steps/sec on HornsRev1 (80 turbines in the reference's
+data_cases.py:269-291; README/BASELINE.json say 76), FP32 fast mode, env batch sharded over the GPUs of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA kernels through the C-ABI)
+    python bench.py --impl reference [--gpus N] ...                 # the reference's CPU path (oracle port, all cores)
+
+For N > 1 launch under torchrun (one rank per GPU).  Rank 0 prints ONE JSON line.
+A "step" = one env step (constraint + yaw transition + full FLORIS GCH wake solve + measures + reward) for EVERY env of
+the batch.  No collective in the step; NCCL only all-gathers the per-rank episode-return statistics at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYOUT = "HornsRev1_"
+ENVS_PER_GPU = 8192          # BASELINE.json configs[4]: 65536 envs over 8 GPUs
+MAX_NUM_STEPS = 500          # simple_env.py:24 default episode length (truncation at step 499)
+L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# canonical algorithmic work per env-step (SURVEY.md section 8d / BASELINE.md section 4)
+# ------------------------------------------------------------------------------------------------------------------
+def canonical_work(T: int):
+    n_pp = 9 * T * (T - 1) // 2
+    w_fp32 = 121 * n_pp + 950 * T
+    w_sp = 23.2 * n_pp + 190 * T
+    return w_fp32, w_sp
+
+
+def algorithmic_bytes(T: int) -> int:
+    return 48 * T + 16
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# nvidia-smi clock sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax.append(mx)
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # timed region shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.lines:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                except Exception:
+                    pass
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's Python+FLORIS step (numpy, same op structure), all host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(conn, layout, seed):
+    sys.path.insert(0, ROOT)
+    from oracle.env_oracle import EnvOracle
+    from wfcrl_b200.layouts import get_layout
+
+    case = get_layout(layout)
+    env = EnvOracle(case["xcoords"], case["ycoords"], max_num_steps=MAX_NUM_STEPS)
+    rng = np.random.default_rng(seed)
+    env.reset(seed=seed)
+    T = env.num_turbines
+    done_steps = 0
+    conn.send("ready")
+    while True:
+        n = conn.recv()
+        if n <= 0:
+            break
+        t0 = time.perf_counter()
+        for _ in range(n):
+            env.step({"yaw": rng.uniform(-5, 5, T).astype(np.float32)})
+            done_steps += 1
+            if done_steps >= MAX_NUM_STEPS - 1:
+                env.reset(seed=seed + done_steps)
+                done_steps = 0
+        conn.send(time.perf_counter() - t0)
+
+
+class CpuFarm:
+    """`workers` persistent single-env processes of the oracle port (the reference runs one env per process)."""
+
+    def __init__(self, layout: str, workers: int):
+        import multiprocessing as mp
+
+        for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ.setdefault(var, "1")
+        ctx = mp.get_context("spawn")
+        self.workers = workers
+        self.conns, self.procs = [], []
+        for w in range(workers):
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(child, layout, 1000 + w), daemon=True)
+            p.start()
+            self.conns.append(parent)
+            self.procs.append(p)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def run(self, steps_per_worker: int) -> float:
+        """All workers step concurrently; returns aggregate env-steps/s (total steps / slowest worker)."""
+        for c in self.conns:
+            c.send(steps_per_worker)
+        per = [c.recv() for c in self.conns]
+        return self.workers * steps_per_worker / max(per)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(0)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    workers = min(cores, 64)
+    from wfcrl_b200.layouts import get_layout
+
+    T = get_layout(LAYOUT)["num_turbines"]
+    per_step = 2  # env steps per worker per bench "step" (bounded sample: ~0.1-0.2 s per env step at T=80)
+    farm = CpuFarm(LAYOUT, workers)
+    for _ in range(max(args.warmup, 0)):
+        farm.run(1)
+    rates, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        rates.append(farm.run(per_step))
+    wall = time.perf_counter() - t0
+    farm.close()
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "Floris env-steps/sec (HornsRev1)", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"HornsRev1_Floris T={T}, {workers} single-env host processes x {per_step} env steps per "
+                               "bench step, U(-5,5) yaw actions, sampled wind"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": workers, "kind": "port",
+                         "sample": f"{workers} procs x {per_step} steps x {args.steps} repeats of the numpy oracle port "
+                                   "(FLORIS is not installable here; restated oracle, not the reference package)"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from wfcrl_b200.backend import FlorisBatch
+    from wfcrl_b200.layouts import get_layout
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    case = get_layout(LAYOUT)
+    T, B = case["num_turbines"], args.envs_per_gpu
+    precision = args.precision
+    fb = FlorisBatch(case["xcoords"], case["ycoords"], B, device=local, precision=precision, kernel=args.kernel,
+                     max_iter=MAX_NUM_STEPS)
+    real = torch.float64 if precision == "f64" else torch.float32
+
+    # synthetic wind-condition stream: the reference's reset distribution (mdp.py:242-258), keyed by the GLOBAL env id so
+    # that 1/2/4/8-GPU runs see identical per-env streams
+    gid0 = rank * B
+    ws = np.empty(B)
+    wd = np.empty(B)
+    for b in range(B):
+        rng = np.random.default_rng(gid0 + b)
+        ws[b] = np.clip(8 * rng.weibull(8), 3, 28)
+        wd[b] = np.clip(rng.normal(270, 20) % 360, 0, 360)
+    d_ws, d_wd = torch.as_tensor(ws, device=dev), torch.as_tensor(wd, device=dev)
+    all_mask = torch.ones(B, dtype=torch.uint8, device=dev)
+
+    # synthetic yaw-action stream U(-5, 5), a pool of distinct device buffers cycled through
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    pool = [(torch.rand(B, T, device=dev, generator=gen) * 10 - 5).contiguous() for _ in range(8)]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    fb.reset(ws, wd, host_trig=False)
+    steps_in_episode = 0
+    returns = torch.zeros(B, dtype=torch.float64, device=dev)
+
+    def env_step(k):
+        nonlocal steps_in_episode
+        out = fb.step(pool[k % len(pool)])
+        steps_in_episode += 1
+        if steps_in_episode >= MAX_NUM_STEPS - 1:  # every env truncates together: device-side reset, new episode
+            fb.reset_masked(all_mask, d_ws, d_wd)
+            steps_in_episode = 0
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 3)):
+        env_step(k)
+    barrier()
+
+    # ---- timed region: K steps, L2 flushed before each, CUDA events on the launching stream -----------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = fb.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        out = env_step(k)
+        ev[k][1].record()
+        returns += out["reward"].double()
+    barrier()
+    t_wall1 = time.time()
+    launches = fb.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- end-to-end: host buffers, H2D + step + D2H inside the timed region -----------------------------------------
+    host_pool = [p.cpu().pin_memory() for p in pool[:4]]
+    e2e_steps = max(3, min(args.steps, 20))
+    fb.step_host(host_pool[0])
+    barrier()
+    e0 = time.perf_counter()
+    for k in range(e2e_steps):
+        res = fb.step_host(host_pool[k % len(host_pool)])
+        steps_in_episode += 1
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    h2d, d2h = fb.last_h2d_bytes, fb.last_d2h_bytes
+    _ = float(res["reward"][0])
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------------
+    stats = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        # the only collective of the job: all-gather of per-rank episode-return statistics (north_star)
+        mine = torch.stack([returns.mean(), returns.std()]).to(torch.float64)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        mean_return = float(torch.stack(gathered)[:, 0].mean())
+    else:
+        mean_return = float(returns.mean())
+    total_ms, e2e_s = float(stats[0]), float(stats[1])
+
+    if rank == 0:
+        info = fb.device_info()
+        value = world * B * args.steps / (total_ms / 1e3)
+        per_gpu = value / world
+        w_fp32, w_sp = canonical_work(T)
+        sm_max_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, peak_src = 6650.0, "fallback"
+        if os.path.exists(peaks_path):
+            try:
+                hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+            except Exception:
+                pass
+        fp32_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6
+        mufu_peak = info["sm_count"] * 16 * sm_max_mhz * 1e6
+        fp32_ach = per_gpu * (w_fp32 + w_sp)
+        mufu_ach = per_gpu * w_sp
+        hbm_ach = per_gpu * algorithmic_bytes(T) / 1e9
+        roofline = {
+            "bound": "fp32_issue", "kernel": "wf_step_fast_kernel" if args.kernel == "fast" else "wf_step_basic_kernel",
+            "achieved": fp32_ach / 1e9, "peak": fp32_peak / 1e9, "unit": "G lane-op/s", "frac": fp32_ach / fp32_peak,
+            "frac_at_observed_clock": fp32_ach / (info["sm_count"] * 128 * sm_mhz * 1e6),
+            "peak_basis": f"{info['sm_count']} SMs x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (clocks.max.sm); canonical work "
+                          f"{w_fp32 + w_sp:.0f} lane-ops per env-step (SURVEY 8d), not the instructions actually issued",
+            "mufu": {"achieved": mufu_ach / 1e9, "peak": mufu_peak / 1e9, "frac": mufu_ach / mufu_peak,
+                     "unit": "G special/s"},
+            "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "frac": hbm_ach / hbm_peak, "unit": "GB/s",
+                    "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
+            "traffic": None,
+            "avg_launch_ms": total_ms / max(launches, 1),
+            "occupancy": info,
+        }
+        line = {
+            "metric": "Floris env-steps/sec (HornsRev1)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "f32" else "f64", "data": "synthetic",
+            "config": {"workload": f"HornsRev1_Floris, T={T} turbines (reference data_cases.py has 80; README says 76), "
+                                   f"{B} envs per GPU x {world} GPU(s), U(-5,5) yaw actions, wind sampled per env from "
+                                   f"the reference reset distribution, {MAX_NUM_STEPS}-step episodes",
+                       "envs_per_gpu": B, "turbines": T, "precision": precision, "kernel": args.kernel,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
+                       "parallelism": f"env-sharded x{world}, no collective in the step"},
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "path": "FlorisBatch.step_host -> wf_step_host (pinned host action in, full step result out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "mean_episode_return_so_far": mean_return,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            workers = min(cores, 64)
+            t0 = time.perf_counter()
+            farm = CpuFarm(LAYOUT, workers)
+            farm.run(1)
+            rate = farm.run(20)
+            farm.close()
+            wall = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "env-steps/s", "cores": workers, "kind": "port",
+                "sample": f"{workers} single-env processes x 20 HornsRev1 env steps of the numpy oracle port "
+                          f"(wall {wall:.1f} s incl. process start)"}
+        print(json.dumps(line), flush=True)
+    fb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--kernel", default="fast", choices=["fast", "basic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.precision == "f64":
+        args.kernel = "basic"
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
