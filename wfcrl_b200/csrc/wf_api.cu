@@ -11,13 +11,6 @@
 #include <string>
 #include <vector>
 
-// tuned FP32 kernel (wf_fast.cu)
-cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
-                                const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out, int sm_count,
-                                cudaStream_t stream);
-cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
-                                    int* smem);
-
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
     g_err = msg;
@@ -33,6 +26,7 @@ static int set_err(int code, const std::string& msg) {
 struct WfHandle_t {
     WfConfig cfg;
     WfModel model;
+    WfFastConst fast;
     WfState st;
     int device = 0;
     int sm_count = 0, sm_clock_khz = 0;
@@ -65,6 +59,96 @@ template <typename T> static int dev_alloc(WfHandle_t* h, T** p, size_t n) {
         int _r = (expr);          \
         if (_r != WF_OK) return _r; \
     } while (0)
+
+
+// Host-side (FP64) precomputation of the tuned FP32 kernel's per-model constants.
+static void build_fast_const(const WfConfig& c, WfFastConst* f) {
+    memset(f, 0, sizeof(*f));
+    const double PI = 3.141592653589793, NUM_EPS = 0.001;
+    const double D = c.rotor_diameter, HH = c.hub_height, eps = 0.2 * D, eps2 = eps * eps, off = 0.5 * D / 2;
+    double Z[3], ratio[3], rsum = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        Z[k] = HH + (k - 1) * off;
+        ratio[k] = pow(Z[k] / HH, c.wind_shear);
+        rsum += ratio[k];
+    }
+    const double mean_ratio = rsum / 3.0;
+    f->mean_ratio = (float)mean_ratio;
+    const double zc[6] = {-(HH + D / 2), -(HH - D / 2), (HH + D / 2), (HH - D / 2), -HH, HH};
+    double zz[6][3];
+    for (int k = 0; k < 3; ++k) {
+        f->ratio[k] = (float)ratio[k];
+        const double dU = c.wind_shear * pow(1.0 / HH, c.wind_shear) * pow(Z[k], c.wind_shear - 1.0);  // per unit ws
+        const double lmda = D / 8, kappa = 0.41;
+        const double lm = kappa * Z[k] / (1 + kappa * Z[k] / lmda);
+        f->nu4[k] = (float)(4 * lm * lm * fabs(dU) / mean_ratio);
+        for (int q = 0; q < 6; ++q) {
+            zz[q][k] = (Z[k] + zc[q]) + NUM_EPS;
+            f->zz[q][k] = (float)zz[q][k];
+            f->zz2[q][k] = (float)(zz[q][k] * zz[q][k]);
+            f->ez[q][k] = (float)exp(-zz[q][k] * zz[q][k] / eps2);
+        }
+        f->dz2[k] = (float)(((k - 1) * off) * ((k - 1) * off));
+        f->offj[k] = (float)((k - 1) * off);
+    }
+    double a_top = 0, a_bot = 0, a_core = 0, sv[3] = {0, 0, 0};
+    for (int p = 0; p < 9; ++p) {
+        const int j = p / 3, k = p % 3;
+        const double yL = (j - 1) * off + NUM_EPS, q = yL * yL;
+        double fq[6];
+        for (int v = 0; v < 6; ++v) {
+            const double r = q + zz[v][k] * zz[v][k];
+            fq[v] = (1 - exp(-r / eps2)) / (2 * PI * r);
+        }
+        a_top += zz[0][k] * fq[0] / 9.0;
+        a_bot += zz[1][k] * fq[1] / 9.0;
+        a_core += zz[4][k] * fq[4] / 9.0;
+        const double cv[3] = {zz[0][k] * fq[0] - zz[2][k] * fq[2], zz[1][k] * fq[1] - zz[3][k] * fq[3],
+                              zz[4][k] * fq[4] - zz[5][k] * fq[5]};
+        const double cw[3] = {-yL * (fq[0] - fq[2]), -yL * (fq[1] - fq[3]), -yL * (fq[4] - fq[5])};
+        for (int v = 0; v < 3; ++v) {
+            f->cv[v][p] = (float)cv[v];
+            f->cw[v][p] = (float)cw[v];
+            sv[v] += cv[v];
+        }
+    }
+    f->a_top = (float)a_top; f->a_bot = (float)a_bot; f->a_core = (float)a_core;
+    for (int v = 0; v < 3; ++v) f->sv[v] = (float)sv[v];
+    f->D = (float)D; f->inv_D = (float)(1.0 / D); f->eps2 = (float)eps2; f->inv_eps2 = (float)(1.0 / eps2);
+    f->inv_2pi = (float)(1.0 / (2 * PI));
+    const double vel_top = pow((HH + D / 2) / HH, c.wind_shear), vel_bot = pow((HH - D / 2) / HH, c.wind_shear);
+    f->c_top = (float)((PI / 8) * D * vel_top * mean_ratio);
+    f->c_bot = (float)((PI / 8) * D * vel_bot * mean_ratio);
+    f->c_wr = (float)(0.25 * 2 * PI * D / c.tsr);
+    f->alpha4 = (float)(4 * c.alpha); f->beta2 = (float)(2 * c.beta); f->ka = (float)c.ka; f->kb = (float)c.kb;
+    f->ad = (float)c.ad; f->bd = (float)c.bd; f->dm03 = (float)(0.3 * c.dm);
+    f->e3_112 = (float)(3 * exp(1.0 / 12.0)); f->e3_13 = (float)(3 * exp(1.0 / 3.0));
+    f->near_c = (float)(0.501 * D * sqrt(0.5));
+    f->d2_8 = (float)(D * D / 8.0);
+    f->ch_const = (float)c.ch_constant; f->ch_ai = (float)c.ch_ai; f->ch_init = (float)c.ch_initial;
+    f->ch_down = (float)c.ch_downstream;
+    f->pP3 = (float)(c.pP / 3.0); f->rho_fac = (float)cbrt(c.air_density / c.ref_density_cp_ct);
+    f->ref_rho = (float)c.ref_density_cp_ct; f->two_D = (float)(2 * D);
+    f->load_coef = (float)c.load_coef; f->shaper_reference = (float)c.shaper_reference;
+    const int n = c.table_len;
+    f->table_len = n;
+    const double area = PI * pow(D / 2.0, 2.0);
+    for (int i = 0; i < n; ++i) {
+        f->tab_ws[i] = (float)c.table_ws[i];
+        f->tab_ct[i] = (float)c.table_ct[i];
+        f->tab_pw[i] = (float)(0.5 * area * c.table_cp[i] * c.generator_efficiency * pow(c.table_ws[i], 3.0));
+    }
+    f->coarse_len = 128;
+    const double span = c.table_ws[n - 1] - c.table_ws[0];
+    f->coarse_scale = (float)(128.0 / span);
+    for (int bkt = 0; bkt < 128; ++bkt) {
+        // conservative (slightly early) left edge so that float rounding of the bucket index can never skip a node
+        const double left = c.table_ws[0] + (bkt - 0.01) * span / 128.0;
+        int idx = 0;
+        while (idx + 1 < n - 1 && c.table_ws[idx + 1] <= left) ++idx;
+        f->coarse[bkt] = (unsigned char)idx;
+    }
+}
 
 extern "C" {
 
@@ -171,6 +255,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         ymin = fmin(ymin, ly[t]); ymax = fmax(ymax, ly[t]);
     }
     m.xc = (xmin + xmax) / 2; m.yc = (ymin + ymax) / 2;
+    build_fast_const(*cfg, &h->fast);
 
     int rc = WF_OK;
     auto fail = [&](int r) { wf_destroy(h); return r; };
@@ -201,7 +286,8 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
         (rc = dev_alloc(h, &s.xi, BT)) || (rc = dev_alloc(h, &s.yi, BT)) || (rc = dev_alloc(h, &s.order, BT)) ||
-        (rc = dev_alloc(h, &s.cs, (size_t)2 * B)) || (rc = dev_alloc(h, &h->d_mask, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.cs, (size_t)2 * B)) || (rc = dev_alloc(h, &s.xhl, BT)) ||
+        (rc = dev_alloc(h, &s.yhl, BT)) || (rc = dev_alloc(h, &s.idx, BT)) || (rc = dev_alloc(h, &h->d_mask, (size_t)B)) ||
         (rc = dev_alloc(h, &h->d_rws, (size_t)B)) || (rc = dev_alloc(h, &h->d_rwd, (size_t)B)) ||
         (rc = dev_alloc(h, &h->d_rcs, (size_t)2 * B)))
         return fail(rc);
@@ -243,7 +329,7 @@ static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float*
                        const WfOutPtrs& out, cudaStream_t st) {
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST)
-        e = wf_launch_step_fast(mode, h->model, h->st, d_mask, d_action, d_yaw, out, h->sm_count, st);
+        e = wf_launch_step_fast(mode, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, st);
     else
         e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, st);
     h->launches += 1;

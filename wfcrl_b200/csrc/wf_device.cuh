@@ -44,6 +44,38 @@ struct WfState {
     double* yi;         // [B][T] np.mean of the 9 grid y values (numpy reduction order)
     int* order;         // [B][T] sorted position -> original turbine index
     double* cs;         // [B][2] cosd/sind of the deviation from west actually used
+    // FP32 fast-kernel geometry: positions relative to the rotation centre as float-float pairs and, per SOURCE
+    // position i, the first sorted target index for which each FP64 x-mask of SURVEY A.7/A.8 becomes true
+    float2* xhl;        // [B][T] (hi, lo) of xs - xc
+    float2* yhl;        // [B][T] (hi, lo) of ys - yc
+    uchar4* idx;        // [B][T] .x: first t with X[t]-x_i >= 0 ; .y: first t with X[t] > x_i+0.1 ;
+                        //         .z: first t with X[t] > x_i ; .w: first t with X[t] > x_i+15D   (T if none)
+};
+
+// Constants of the tuned FP32 kernel, precomputed on the host in FP64 (wf_api.cu: build_fast_const).
+struct WfFastConst {
+    float ratio[3];        // (Z_k / HH)^shear : U0[k] = ws * ratio[k]
+    float mean_ratio;      // Uinf = ws * mean_ratio
+    float nu4[3];          // 4 * nu_k / Uinf (independent of ws)
+    float zz[6][3];        // Z_k + c_v + NUM_EPS, vortices in FLORIS order V1..V6 (see wf_kernels.cu transverse())
+    float zz2[6][3];       // zz^2
+    float ez[6][3];        // exp(-zz^2 / eps^2)
+    float a_top, a_bot, a_core;   // secondary steering: mean over the own grid of z/(2 pi r) * core per unit circulation
+    float cv[3][9], cw[3][9];     // self-induced V / W per unit (Gt, Gb, Gwr) on the own grid
+    float sv[3];                  // sum over the 9 points of cv
+    float D, inv_D, eps2, inv_eps2, inv_2pi;
+    float c_top, c_bot, c_wr;     // G_top0 = c_top*ws*ct ; G_bot0 = c_bot*ws*ct ; Gwr = c_wr*(a-a^2)*avg
+    float alpha4, beta2, ka, kb, ad, bd, dm03, e3_112, e3_13;
+    float near_c;                 // 0.501 * D * sqrt(1/2)
+    float d2_8;                   // D^2 / 8
+    float ch_const, ch_ai, ch_init, ch_down;
+    float pP3, rho_fac, ref_rho, two_D, offj[3], dz2[3];
+    float load_coef, shaper_reference;
+    int table_len;
+    float tab_ws[64], tab_ct[64], tab_pw[64];
+    unsigned char coarse[128];    // coarse[floor(x * coarse_scale)] = table interval containing that bucket's left edge
+    float coarse_scale;
+    int coarse_len;
 };
 
 struct WfOutPtrs {
@@ -68,3 +100,8 @@ cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, cons
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                   const double* d_wd, cudaStream_t stream);
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);
+cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
+                                const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                const WfOutPtrs& out, cudaStream_t stream);
+cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+                                    int* smem);

@@ -1,17 +1,465 @@
-// Tuned FP32 step kernel (placeholder: forwards to the basic FP32 kernel until the tuned variant lands).
+// Tuned FP32 step kernel for sm_100a: ONE WARP PER ENVIRONMENT (CTA = 32 threads = one env / wind condition).
+//
+// Design (DESIGN.md "fast kernel"):
+//  * the whole per-env solver state lives in shared memory: for every rotor grid point the running sum of squared
+//    velocity deficits (SOSFS), v and w; per turbine the running maximum of the wake-added turbulence, the rotated
+//    coordinates as float-float pairs and the precomputed FP64 mask indices.  ~12.9 KB per env at T = 80, so 16 envs
+//    are resident per SM and no block-level barrier exists anywhere (only __syncwarp).
+//  * sequential solver over sources i; for each source every lane first computes the (warp-uniform) source
+//    prologue redundantly -- no cross-lane traffic -- then the warp sweeps the downstream targets in passes of
+//    10 turbines x 3 lateral grid columns (30 of 32 lanes busy); each lane handles the 3 vertical points of its
+//    column, so deflection, wake widths and the lateral Gaussian are evaluated once per column.
+//  * x-direction masks are NOT evaluated in floating point here: the geometry kernel (FP64) stores, per source,
+//    the first target index at which each mask turns true, so the kernel is FP64-free.
+//  * algebra legal in FP32 mode only: exp(-(y^2+z^2)/eps^2) = exp(-y^2/eps^2) * const_z, paired reciprocals,
+//    uR/(U0+u0) = 1/2, self-induced vortex velocities and the secondary-steering integrals as per-model constants,
+//    sum of squares instead of a hypot chain.
+//
+// Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
+// wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
 #include "wf_device.cuh"
 
-cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
-                                const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out, int sm_count,
-                                cudaStream_t stream) {
-    (void)sm_count;
-    return wf_launch_step_basic(1, mode, m, s, d_mask, d_action, d_yaw_cmd, out, stream);
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kDeg = 57.29577951308232f;
+constexpr float kRad = 0.017453292519943295f;
+constexpr float kNumEpsF = 0.001f;
+constexpr int kTurbPerPass = 10;
+
+__device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float flg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fclamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// piecewise-linear table lookup (np.interp + scipy fill values), warp-uniform or per-lane x
+__device__ __forceinline__ float interp_f(const WfFastConst& fc, const float* __restrict__ fp, float x, float left,
+                                          float right) {
+    const int n = fc.table_len;
+    const float x0 = fc.tab_ws[0], xn = fc.tab_ws[n - 1];
+    if (x < x0) return left;
+    if (x > xn) return right;
+    int bkt = (int)((x - x0) * fc.coarse_scale);
+    bkt = min(bkt, fc.coarse_len - 1);
+    int idx = fc.coarse[bkt];
+    while (idx + 1 < n - 1 && fc.tab_ws[idx + 1] <= x) ++idx;
+    const float xa = fc.tab_ws[idx], fa = fp[idx];
+    const float slope = (fp[idx + 1] - fa) * frcp(fc.tab_ws[idx + 1] - xa);
+    return fmaf(slope, x - xa, fa);
+}
+
+struct SmemView {
+    float *wsq, *v, *w;       // [9T] per rotor point, q = 9 t + 3 j + k
+    float2 *xhl, *yhl;        // [T]
+    float *tia;               // [3T] running max of the wake-added TI per (turbine, lateral column)
+    float *cyaw, *syaw, *yawr;  // [T] cos / sin / radians of the yaw (sorted order)
+    float *tifin;             // [T] final rotor-mean TI
+    float *ynew;              // [T] new yaw, degrees, ORIGINAL order
+    uchar4* idx;              // [T]
+    unsigned char* ordr;      // [T]
+};
+
+__host__ __device__ inline size_t fast_smem_bytes(int T) {
+    size_t n = 0;
+    n += (size_t)3 * 9 * T * 4;  // wsq, v, w
+    n += (size_t)2 * T * 8;      // xhl, yhl
+    n += (size_t)3 * T * 4;      // tia
+    n += (size_t)5 * T * 4;      // cyaw, syaw, yawr, tifin, ynew
+    n += (size_t)T * 4;          // idx
+    n += (size_t)((T + 15) / 16 * 16);
+    return (n + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
+    SmemView s;
+    float2* f2 = (float2*)base;
+    s.xhl = f2;
+    s.yhl = f2 + T;
+    float* f = (float*)(f2 + 2 * T);
+    s.wsq = f; f += 9 * T;
+    s.v = f; f += 9 * T;
+    s.w = f; f += 9 * T;
+    s.tia = f; f += 3 * T;
+    s.cyaw = f; f += T;
+    s.syaw = f; f += T;
+    s.yawr = f; f += T;
+    s.tifin = f; f += T;
+    s.ynew = f; f += T;
+    s.idx = (uchar4*)f; f += T;
+    s.ordr = (unsigned char*)f;
+    return s;
+}
+
+__global__ void __launch_bounds__(32, 16)
+wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfFastConst fc, const WfState s,
+                    const uint8_t* __restrict__ mask, const float* __restrict__ action,
+                    const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    const int lane = threadIdx.x;
+    const size_t row = (size_t)b * T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemView sm = carve(smem_raw, T);
+
+    // ---- env prologue on the ORIGINAL turbine order (mdp.py:291-319, simple_env.py:64-72) -------------------------
+    int nm = 0;
+    if (mode == WF_MODE_ENV) nm = s.num_moves[b] + 1;
+    for (int tt = lane; tt < T; tt += 32) {
+        float ynew;
+        if (mode == WF_MODE_ENV) {
+            float a = action[row + tt];
+            const float acc = s.acc[row + tt];
+            const float acc_c = (m.multi_agent && tt != T - 1) ? s.acc_prev[row + tt] : acc;
+            const float frac = __fdiv_rn(__fdiv_rn(__fdiv_rn(acc_c, m.rate_f), (float)nm), m.dt_f);
+            if (frac >= 0.1f) a = 0.0f;
+            if (m.continuous) a = fminf(fmaxf(a, -m.yaw_step_f), m.yaw_step_f);
+            else a = __fmul_rn(__fsub_rn(a, 1.0f), m.yaw_step_f);
+            const float y0 = fminf(fmaxf((float)s.yaw[row + tt], m.yaw_lo_f), m.yaw_hi_f);
+            ynew = fminf(fmaxf(__fadd_rn(y0, a), m.yaw_lo_f), m.yaw_hi_f);
+            s.acc_prev[row + tt] = acc;
+            s.acc[row + tt] = __fadd_rn(acc, fabsf(a));
+            s.yaw[row + tt] = (double)ynew;
+        } else if (mode == WF_MODE_INTERFACE && yaw_cmd) {
+            const double y = yaw_cmd[row + tt];
+            s.yaw[row + tt] = y;
+            ynew = (float)y;
+        } else {
+            ynew = (float)s.yaw[row + tt];
+        }
+        sm.ynew[tt] = ynew;
+        sm.xhl[tt] = s.xhl[row + tt];
+        sm.yhl[tt] = s.yhl[row + tt];
+        sm.idx[tt] = s.idx[row + tt];
+        sm.ordr[tt] = (unsigned char)s.order[row + tt];
+    }
+    for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.f; sm.v[q] = 0.f; sm.w[q] = 0.f; }
+    for (int q = lane; q < 3 * T; q += 32) sm.tia[q] = 0.f;
+    __syncwarp();
+    for (int tt = lane; tt < T; tt += 32) {
+        const float yr = sm.ynew[sm.ordr[tt]] * kRad;
+        float sy, cy;
+        sincosf(yr, &sy, &cy);
+        sm.yawr[tt] = yr;
+        sm.cyaw[tt] = cy;
+        sm.syaw[tt] = sy;
+    }
+    // per-env constants (warp-uniform registers)
+    const double ws_d = s.ws[b], wd_d = s.wd[b];
+    const float ws = (float)ws_d;
+    const float I0 = (float)s.ti_amb[b];
+    const float I02 = I0 * I0;
+    const float I0p = __powf(I0, fc.ch_init);
+    const float U0a = ws * fc.ratio[0], U0b = ws * fc.ratio[1], U0c = ws * fc.ratio[2];
+    const float D = fc.D;
+    __syncwarp();
+
+    // lane -> (turbine slot g in the pass, lateral column j); each lane owns the 3 vertical points k of its column
+    const int g = lane / 3, j = lane - 3 * g;
+    const bool lane_ok = lane < 3 * kTurbPerPass;
+    const float offj = (j == 0) ? fc.offj[0] : ((j == 1) ? fc.offj[1] : fc.offj[2]);
+
+    // ---- sequential solver over sources -------------------------------------------------------------
+    for (int i = 0; i < T; ++i) {
+        // ===== source prologue: every lane computes the same values =====
+        float wq[9], vq[9], wwq[9];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) { wq[p] = sm.wsq[9 * i + p]; vq[p] = sm.v[9 * i + p]; wwq[p] = sm.w[9 * i + p]; }
+        float su3 = 0.f, sv = 0.f, sw = 0.f;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            const float U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
+            const float u = U0k - fsqrt(wq[p]);
+            su3 = fmaf(u * u, u, su3);
+            sv += vq[p];
+            sw += wwq[p];
+        }
+        const float avg = cbrtf(su3 * (1.f / 9.f));
+        const float ct_raw = fclamp(interp_f(fc, fc.tab_ct, avg, 0.0001f, 0.9999f), 0.0001f, 0.9999f);
+        const float cy = sm.cyaw[i], sy = sm.syaw[i], yr = sm.yawr[i];
+        const float ct = ct_raw * cy;
+        const float s1c = fsqrt(1.f - ct * cy);
+        const float a = 0.5f * frcp(cy) * (1.f - s1c);
+        const float Gtop0 = fc.c_top * ws * ct, Gbot0 = fc.c_bot * ws * ct;
+        const float Gwr = fc.c_wr * (a - a * a) * avg;
+        const float Gt = sy * cy * Gtop0, Gb = -(sy * cy * Gbot0);
+
+        // A.5 secondary steering through the per-model grid integrals
+        float val = 2.f * (sv * (1.f / 9.f) - Gwr * fc.a_core) * frcp(Gtop0 * fc.a_top - Gbot0 * fc.a_bot);
+        val = fclamp(val, -1.f, 1.f);
+        const float g_rad = -(yr + 0.5f * asinf(val));  // minus the effective yaw, radians
+        const float cg = __cosf(g_rad);
+
+        // A.6 deflection scalars
+        const float sq1ct = fsqrt(1.f - ct);
+        const float sqcg = fsqrt(1.f - ct * cg);
+        const float sz0d = 0.5f * D * fsqrt((1.f + sqcg) * frcp(2.f * (1.f + sq1ct)));
+        const float sy0d = sz0d * cg;
+        const float C0 = 1.f - sq1ct;
+        const float M0 = C0 * (2.f - C0);
+        const float E0 = C0 * C0 - fc.e3_112 * C0 + fc.e3_13;
+        const float th = fc.dm03 * g_rad * frcp(cg) * (1.f - sqcg);
+        const float sM0 = fsqrt(M0);
+        const float tan_th = __sinf(th) * frcp(__cosf(th));
+        const float Kc = th * E0 * (1.f / 5.2f) * fsqrt(sy0d * sz0d * frcp(M0));
+        const float A_ln = (1.6f + sM0) * frcp(1.6f - sM0);
+        const float inv_s0d = frcp(sy0d * sz0d);
+
+        // TI of the source per lateral column before the yaw-added-recovery update
+        const float tp0 = fsqrt(fmaf(sm.tia[3 * i], sm.tia[3 * i], I02));
+        const float tp1 = fsqrt(fmaf(sm.tia[3 * i + 1], sm.tia[3 * i + 1], I02));
+        const float tp2 = fsqrt(fmaf(sm.tia[3 * i + 2], sm.tia[3 * i + 2], I02));
+        const float tpre = (j == 0) ? tp0 : ((j == 1) ? tp1 : tp2);
+        const float beta_term = fc.beta2 * (1.f - sq1ct);
+        const float x0d = D * cg * (1.f + sqcg) * frcp(1.4142135623730951f * fmaf(fc.alpha4, tpre, beta_term));
+        const float kyd = fmaf(fc.ka, tpre, fc.kb);
+        const float inv_x0d = frcp(x0d);
+        const float delta0 = tan_th * x0d;
+        const float Kck = Kc * frcp(kyd);
+
+        // own transverse velocities (A.7 on the source's own grid) + yaw-added recovery (in-place TI update)
+        const uchar4 ix = sm.idx[i];
+        const bool self_on = (int)ix.x <= i;  // X_i - x_i >= 0
+        float sumV = sv, sumW = sw;
+        if (self_on) {
+            sumV += Gt * fc.sv[0] + Gb * fc.sv[1] + Gwr * fc.sv[2];
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                const float Vs = Gt * fc.cv[0][p] + Gb * fc.cv[1][p] + Gwr * fc.cv[2][p];
+                const float Ws = fmaxf(Gt * fc.cw[0][p] + Gb * fc.cw[1][p] + Gwr * fc.cw[2][p], 0.f);
+                sumW += Ws;
+                if (lane == p) { sm.v[9 * i + p] = vq[p] + Vs; sm.w[9 * i + p] = wwq[p] + Ws; }
+            }
+        }
+        const float aI = avg * tp0;
+        const float kk2 = 3.f * aI * aI;  // u_term^2 = 2 k = 2 (avg I)^2 / (2/3)
+        const float v_term = sumV * (1.f / 9.f), w_term = sumW * (1.f / 9.f);
+        const float k_total = 0.5f * (kk2 + v_term * v_term + w_term * w_term);
+        const float I_mix = fsqrt((2.f / 3.f) * k_total) * frcp(avg) - tp0;
+        const float tq0 = fmaf(2.f, I_mix, tp0), tq1 = fmaf(2.f, I_mix, tp1), tq2 = fmaf(2.f, I_mix, tp2);
+        if (lane == 0) sm.tifin[i] = (tq0 + tq1 + tq2) * (1.f / 3.f);
+        const float tpost = (j == 0) ? tq0 : ((j == 1) ? tq1 : tq2);
+
+        // A.8 velocity-model scalars with the updated TI (cos(-yaw) = cy ; sigma_z0 = D / (2 sqrt 2) exactly)
+        const float x0v = D * cy * (1.f + sq1ct) * frcp(1.4142135623730951f * fmaf(fc.alpha4, tpost, beta_term));
+        const float kyv = fmaf(fc.ka, tpost, fc.kb);
+        const float inv_x0v = frcp(x0v);
+        const float sz0v = fc.near_c * (0.5f / 0.501f);  // 0.5 D sqrt(1/2)
+        const float sy0v = sz0v * cy;
+        const float near_s = fc.near_c * fsqrt(ct);
+        const float ctc = ct * cy * fc.d2_8;
+        const float watK = fc.ch_const * __powf(a, fc.ch_ai) * I0p;
+
+        const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
+        const float2 xi = sm.xhl[i], yi = sm.yhl[i];
+
+        // ===== sweep of the downstream targets: 10 turbines x 3 lateral columns per pass =====
+        for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
+            const int t = t0 + g;
+            const bool active = lane_ok && t < T && t != i;
+            int c = 0;
+            float dx = 0.f, dyc = 0.f;
+            if (active) {
+                const float2 xt = sm.xhl[t], yt = sm.yhl[t];
+                dx = (xt.x - xi.x) + (xt.y - xi.y);
+                dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
+                const float lin = fmaf(fc.bd, dx, fc.ad);
+
+                // -- deflection of source i's wake at this column (both branches, select)
+                float defl;
+                {
+                    const float dd = dx - x0d;
+                    const float sgy = fmaf(kyd, dd, sy0d), sgz = fmaf(kyd, dd, sz0d);
+                    const float sq = fsqrt(sgy * sgz * inv_s0d);
+                    const float L = flg2(A_ln * fmaf(1.6f, sq, -sM0) * frcp(fmaf(1.6f, sq, sM0))) * kLn2;
+                    const float d_far = fmaf(Kck, L, delta0) + lin;
+                    const float d_near = fmaf(dx * inv_x0d, delta0, lin);
+                    defl = (dx <= x0d) ? d_near : d_far;
+                }
+                // -- Gaussian deficit: widths and the lateral factor once per column
+                float base, ek;
+                {
+                    const bool far = dx >= x0v;
+                    const bool near = (t >= near_i) && !far;
+                    const float dd = dx - x0v;
+                    const float up = dx * inv_x0v, down = 1.f - up;
+                    const float sgy = far ? fmaf(kyv, dd, sy0v) : fmaf(down, near_s, up * sy0v);
+                    const float sgz = far ? fmaf(kyv, dd, sz0v) : fmaf(down, near_s, up * sz0v);
+                    const float ry = frcp(sgy), rz = frcp(sgz);
+                    const float dy = dyc - defl;
+                    const float ay = 0.5f * (dy * ry) * (dy * ry);
+                    const float dcl = fclamp(1.f - ctc * ry * rz, 0.f, 1.f);
+                    const float C = 1.f - fsqrt(dcl);
+                    base = (near || far) ? C * fex2(-ay * kLog2e) : 0.f;
+                    ek = fex2(-(0.5f * kLog2e) * fc.dz2[0] * rz * rz);
+                }
+                const float dU0 = base * ek * U0a, dU1 = base * U0b, dU2 = base * ek * U0c;
+                c = (dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f);
+
+                // -- transverse velocities of the 6 vortices at the 3 vertical points
+                const float yL = dyc + kNumEpsF;
+                const float q = yL * yL;
+                const float E = fex2(-q * fc.inv_eps2 * kLog2e);
+                float Vk[3], Wk[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float r0 = q + fc.zz2[0][k], r1 = q + fc.zz2[1][k], r2 = q + fc.zz2[2][k];
+                    const float r3 = q + fc.zz2[3][k], r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
+                    const float i02 = frcp(r0 * r2), i13 = frcp(r1 * r3), i45 = frcp(r4 * r5);
+                    const float f0 = fmaf(-E, fc.ez[0][k], 1.f) * (r2 * i02);
+                    const float f2 = fmaf(-E, fc.ez[2][k], 1.f) * (r0 * i02);
+                    const float f1 = fmaf(-E, fc.ez[1][k], 1.f) * (r3 * i13);
+                    const float f3 = fmaf(-E, fc.ez[3][k], 1.f) * (r1 * i13);
+                    const float f4 = fmaf(-E, fc.ez[4][k], 1.f) * (r5 * i45);
+                    const float f5 = fmaf(-E, fc.ez[5][k], 1.f) * (r4 * i45);
+                    const float SV = Gt * fmaf(fc.zz[0][k], f0, -fc.zz[2][k] * f2) +
+                                     Gb * fmaf(fc.zz[1][k], f1, -fc.zz[3][k] * f3) +
+                                     Gwr * fmaf(fc.zz[4][k], f4, -fc.zz[5][k] * f5);
+                    const float SW = Gt * (f0 - f2) + Gb * (f1 - f3) + Gwr * (f4 - f5);
+                    const float dec = fc.eps2 * fc.inv_2pi * frcp(fmaf(fc.nu4[k], dx, fc.eps2));
+                    Vk[k] = SV * dec;
+                    Wk[k] = fmaxf(-yL * SW * dec, 0.f);
+                }
+                // -- state update of this column's 3 points
+                const int qb = 9 * t + 3 * j;
+                sm.wsq[qb] = fmaf(dU0, dU0, sm.wsq[qb]);
+                sm.wsq[qb + 1] = fmaf(dU1, dU1, sm.wsq[qb + 1]);
+                sm.wsq[qb + 2] = fmaf(dU2, dU2, sm.wsq[qb + 2]);
+                sm.v[qb] += Vk[0]; sm.v[qb + 1] += Vk[1]; sm.v[qb + 2] += Vk[2];
+                sm.w[qb] += Wk[0]; sm.w[qb + 1] += Wk[1]; sm.w[qb + 2] += Wk[2];
+            }
+            // -- Crespo-Hernandez wake-added TI: overlap = (#points with deficit*U0 > 0.05) / 9 over the 3 columns
+            const int gb = 3 * g;
+            const int c_tot = __shfl_sync(0xffffffffu, c, gb & 31) + __shfl_sync(0xffffffffu, c, (gb + 1) & 31) +
+                              __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
+            if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabsf(dyc) < fc.two_D) {
+                const float wat = watK * __powf(dx * fc.inv_D, fc.ch_down);
+                const float ta = (float)c_tot * (1.f / 9.f) * wat;
+                sm.tia[3 * t + j] = fmaxf(sm.tia[3 * t + j], ta);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue: lane = sorted turbine; measures, power, loads (interface.py:565-577, 622-648) ------------------
+    const bool env = (mode != WF_MODE_INTERFACE);
+    const float wd = (float)wd_d;
+    float rsum_p = 0.f, rsum_l = 0.f;
+    for (int tt = lane; tt < T; tt += 32) {
+        float u[9], vv[9], ww[9];
+        float su = 0.f, su3 = 0.f, svv = 0.f, sww = 0.f, sdd = 0.f;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            const float U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
+            u[p] = U0k - fsqrt(sm.wsq[9 * tt + p]);
+            vv[p] = sm.v[9 * tt + p];
+            ww[p] = sm.w[9 * tt + p];
+            su += u[p];
+            su3 = fmaf(u[p] * u[p], u[p], su3);
+            svv += vv[p];
+            sww += ww[p];
+            sdd += atan2f(vv[p], u[p]);
+        }
+        const float avg = cbrtf(su3 * (1.f / 9.f));
+        const float mu = su * (1.f / 9.f), mv = svv * (1.f / 9.f), mw = sww * (1.f / 9.f);
+        float qu = 0.f, qv = 0.f, qw = 0.f;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            qu = fmaf(u[p] - mu, u[p] - mu, qu);
+            qv = fmaf(vv[p] - mv, vv[p] - mv, qv);
+            qw = fmaf(ww[p] - mw, ww[p] - mw, qw);
+        }
+        const float veff = fc.rho_fac * avg * __powf(sm.cyaw[tt], fc.pP3);
+        const float pw = interp_f(fc, fc.tab_pw, veff, 0.f, 0.f) * fc.ref_rho;  // [W]
+        float wsl = avg;
+        float wdl = wd - kDeg * sdd * (1.f / 9.f);
+        float loads[4] = {sm.tifin[tt], fsqrt(qu * (1.f / 9.f)), fsqrt(qv * (1.f / 9.f)), fsqrt(qw * (1.f / 9.f))};
+        float p_out;
+        if (env) {
+            p_out = pw * 1e-6f;
+            rsum_p += p_out;
+            rsum_l += fabsf(loads[0]) + fabsf(loads[1]) + fabsf(loads[2]) + fabsf(loads[3]);
+        } else {
+            p_out = pw;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) loads[q] *= 1e7f;
+        }
+        const int orig = sm.ordr[tt];
+        float yv = sm.ynew[orig];
+        if (mode == WF_MODE_WARMUP) {  // start state is clipped to the observation space (mdp.py:263-266)
+            wsl = fclamp(wsl, 3.f, 28.f);
+            wdl = fclamp(wdl, 0.f, 360.f);
+            yv = fclamp(yv, m.yaw_lo_f, m.yaw_hi_f);
+        }
+        const size_t o = row + orig;
+        if (out.yaw) ((float*)out.yaw)[o] = yv;
+        if (out.wind_speed) ((float*)out.wind_speed)[o] = wsl;
+        if (out.wind_direction) ((float*)out.wind_direction)[o] = wdl;
+        if (out.power) ((float*)out.power)[o] = p_out;
+        if (out.load) ((float4*)out.load)[o] = make_float4(loads[0], loads[1], loads[2], loads[3]);
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        rsum_p += __shfl_xor_sync(0xffffffffu, rsum_p, sft);
+        rsum_l += __shfl_xor_sync(0xffffffffu, rsum_l, sft);
+    }
+    if (lane == 0) {
+        const int it = s.num_iter[b] + 1;
+        s.num_iter[b] = it;
+        if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
+        float fw0 = ws, fw1 = wd;
+        if (mode == WF_MODE_WARMUP) { fw0 = fclamp(fw0, 3.f, 28.f); fw1 = fclamp(fw1, 0.f, 360.f); }
+        if (out.freewind) ((float2*)out.freewind)[b] = make_float2(fw0, fw1);
+        if (mode == WF_MODE_ENV) {
+            s.num_moves[b] = nm;
+            const float wn = (float)s.ws_norm[b];
+            const float invT = 1.f / (float)T;
+            float reward = rsum_p * 1e3f / (wn * wn * wn) * invT - fc.load_coef * rsum_l * (0.25f * invT);
+            if (m.shaper == 1) {
+                reward = (reward - fc.shaper_reference) / fc.shaper_reference;
+            } else if (m.shaper == 2) {
+                const double ref = s.shaper_ref[b];
+                const float shaped = (ref == 0.0) ? 0.f : (float)(((double)reward - ref) / ref);
+                s.shaper_ref[b] = (double)reward;
+                reward = shaped;
+            }
+            if (out.reward) ((float*)out.reward)[b] = reward;
+            s.ws_norm[b] = ws_d;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
+                                const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                const WfOutPtrs& out, cudaStream_t stream) {
+    const size_t smem = fast_smem_bytes(m.T);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    wf_step_fast_kernel<<<m.B, 32, smem, stream>>>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    return cudaGetLastError();
 }
 
 cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem) {
-    *threads = (m.T + 31) / 32 * 32;
-    cudaError_t e = wf_step_basic_attributes(1, attr, ctas_per_sm, *threads);
-    *smem = (int)attr->sharedSizeBytes;
-    return e;
+    *threads = 32;
+    *smem = (int)fast_smem_bytes(m.T);
+    cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(attr, wf_step_fast_kernel);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast_kernel, 32, *smem);
 }

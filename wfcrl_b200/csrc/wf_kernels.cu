@@ -159,7 +159,7 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
     if (mask && !mask[b]) return;
     const int T = m.T;
     const int t = threadIdx.x;
-    __shared__ double xr[WF_MAX_TURBINES_K], yr[WF_MAX_TURBINES_K];
+    __shared__ double xr[WF_MAX_TURBINES_K], yr[WF_MAX_TURBINES_K], xsrt[WF_MAX_TURBINES_K];
     __shared__ double cs[2];
     if (t == 0) {
         double c, sn;
@@ -204,6 +204,28 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
         const double s03 = __dadd_rn(__dadd_rn(ya, ya), __dadd_rn(ya, yb));
         const double s47 = __dadd_rn(__dadd_rn(yb, yb), __dadd_rn(yc, yc));
         s.yi[o] = __ddiv_rn(__dadd_rn(__dadd_rn(s03, s47), yc), 9.0);
+        // float-float positions relative to the rotation centre for the FP32 kernel
+        const double xrel = x - m.xc, yrel = y - m.yc;
+        const float xh = (float)xrel, yh = (float)yrel;
+        s.xhl[o] = make_float2(xh, (float)(xrel - (double)xh));
+        s.yhl[o] = make_float2(yh, (float)(yrel - (double)yh));
+        xsrt[rank] = x;
+    }
+    __syncthreads();
+    if (t < T) {
+        // t is now a SORTED source position: first target index at which each FP64 x-mask turns true
+        const size_t o = (size_t)b * T + t;
+        const double x_i = s.xi[o];
+        const double x01 = __dadd_rn(x_i, 0.1), x15 = __dadd_rn(15 * m.D, x_i);
+        int i0 = T, i1 = T, i2 = T, i3 = T;
+        for (int q = T - 1; q >= 0; --q) {
+            const double xq = xsrt[q];
+            if (__dsub_rn(xq, x_i) >= 0.0) i0 = q;
+            if (xq > x01) i1 = q;
+            if (xq > x_i) i2 = q;
+            if (xq > x15) i3 = q;
+        }
+        s.idx[o] = make_uchar4((unsigned char)i0, (unsigned char)i1, (unsigned char)i2, (unsigned char)i3);
     }
 }
 
