@@ -65,3 +65,21 @@ def solve_batch(layout_x, layout_y, ws, wd, yaw_deg, cs=None, ti_ambient=0.06, n
         raise RuntimeError(f"wf_oracle_solve_batch failed rc={rc}")
     out["order"] = order
     return out
+
+
+class _Sol:
+    __slots__ = ("order", "power_W", "ws_local", "wd_local", "ti", "std_u", "std_v", "std_w")
+
+
+def solve(layout_x, layout_y, ws, wd, yaw_deg, *, cs=None, ti_ambient=0.06):
+    """Single-env drop-in for ``floris_oracle.solve`` (same attribute names) backed by the C restatement.  The rotation
+    uses numpy's cosd/sind (passed in) so that the turbine order and self-masks are those of the numpy oracle."""
+    if cs is None:
+        dev = ((np.float64(wd) - 270.0) % 360.0 + 360.0) % 360.0
+        cs = (np.cos(np.radians(dev)), np.sin(np.radians(dev)))
+    out = solve_batch(layout_x, layout_y, [ws], [wd], np.asarray(yaw_deg, dtype=np.float64)[None, :], cs=[cs],
+                      ti_ambient=ti_ambient, nthreads=1)
+    sol = _Sol()
+    for k in _Sol.__slots__:
+        setattr(sol, k, out[k][0])
+    return sol
