@@ -150,8 +150,11 @@ int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, voi
 int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* h_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* Change per-env wind without resetting counters (FlorisInterface.update_wind, interface.py:663-671; time-series
- * mode).  Rebuilds the geometry of the selected envs. d_mask may be NULL (= all). */
-int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, void* stream);
+ * mode, interface.py:503-524,563).  Rebuilds the rotated/sorted geometry of the selected envs.
+ *   d_mask: uint8 [B] or NULL (= all) ; d_ws, d_wd: double [B] (read where selected; wd is reduced % 360)
+ *   d_cs  : double [B][2] host-computed cosd/sind of the deviation from west, or NULL to use the device's FP64 cos/sin */
+int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, const double* d_cs,
+                   void* stream);
 
 /* Per-env ambient turbulence intensity (extension; the reference keeps case.yaml's 0.06). d_ti: double [B]. */
 int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);

@@ -1,0 +1,54 @@
+"""CPU tests of the multi-rank plumbing with the gloo backend, world_size 2 (the step itself has no collective)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wfcrl_b200.dist import gather_episode_stats, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in ((65536, 8), (10, 3), (7, 8), (8192, 1)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(10, rank, world)
+    returns = torch.arange(lo, hi, dtype=torch.float64)  # the "episode return" of global env i is i
+    lengths = torch.full((hi - lo,), 99)
+    stats = gather_episode_stats(returns, lengths)
+    if rank == 0:
+        out.put(stats)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_episode_stats_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    stats = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert stats["episodes"] == 10 and stats["world_size"] == 2
+    assert abs(stats["return_mean"] - 4.5) < 1e-12 and abs(stats["length_mean"] - 99) < 1e-12
+    assert abs(stats["return_std"] - (sum((i - 4.5) ** 2 for i in range(10)) / 10) ** 0.5) < 1e-12
+
+
+def test_single_process_stats():
+    stats = gather_episode_stats(torch.tensor([1.0, 3.0]), torch.tensor([5, 7]))
+    assert stats == {"episodes": 2.0, "return_mean": 2.0, "return_std": 1.0, "length_mean": 6.0, "world_size": 1}

@@ -1,0 +1,213 @@
+"""GPU tests of the host-side mirror of the reference API: ``envs.make`` (Gymnasium / PettingZoo-AEC single envs through
+the FlorisInterface drop-in) and ``envs.make_vec`` (batched), compared with the env-semantics oracle."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, env_oracle
+from tests._util import layout
+
+pytestmark = pytest.mark.gpu
+
+
+def test_make_single_env_reproduces_notebook_flow(cuda_device):
+    """examples/demo.ipynb cells 5-16 with the B200 backend: spaces, reset observation, 69-step episode, history."""
+    from wfcrl_b200 import environments as envs
+
+    env = envs.make("Ablaincourt_Floris", max_num_steps=70)
+    assert env.num_turbines == 7
+    assert "yaw" in env.action_space and env.action_space["yaw"].shape == (7,)
+    assert float(env.action_space["yaw"].low[0]) == -5.0 and env.action_space["yaw"].dtype == np.float32
+    assert list(env.observation_space.keys()) == ["yaw", "freewind_measurements", "wind_speed", "wind_direction"]
+    obs = env.reset(options={"wind_speed": 6.48958384, "wind_direction": 266.363907})
+    assert np.max(np.abs(obs["wind_speed"] - [6.46819497, 4.58929161, 6.46702757, 6.21243961, 6.20072934, 6.1100638,
+                                              5.76785291])) < 2e-8
+    assert np.max(np.abs(obs["wind_direction"] - [266.64538262, 267.04575667, 266.77944635, 266.86120544, 266.89071421,
+                                                  266.92108378, 266.99680007])) < 2e-8
+    lx, ly = layout("Ablaincourt_")
+    ref = env_oracle.EnvOracle(lx, ly, solver=c_oracle.solve, max_num_steps=70)
+    obs = env.reset(seed=3)
+    robs = ref.reset(seed=3)
+    assert np.allclose(obs["freewind_measurements"], robs["freewind_measurements"], rtol=0, atol=0)
+    total, rtotal, i, done = 0.0, 0.0, 0, False
+    while not done:
+        a = np.zeros(7)
+        if i % 5 == 0:
+            a[int(i / 5 % 7)] = -5.0
+        obs, reward, term, trunc, info = env.step({"yaw": a.copy()})
+        robs, rreward, _t, rtrunc, rinfo = ref.step({"yaw": a.copy()})
+        assert np.array_equal(obs["yaw"], robs["yaw"]) and obs["yaw"].dtype == np.float32
+        assert abs(reward[0] - rreward[0]) < 1e-9 * abs(rreward[0])
+        assert np.allclose(info["power"], rinfo["power"], rtol=1e-9, atol=0)
+        assert np.allclose(info["load"], rinfo["load"], rtol=1e-8, atol=1e-12)
+        assert trunc == rtrunc and term is False
+        total += reward
+        rtotal += rreward
+        i += 1
+        done = term or trunc
+    assert i == 69 and len(env.history["observation"]) == 69 and len(env.history["power"]) == 69
+    assert abs(total[0] - rtotal[0]) < 1e-8
+
+
+def test_make_decentralized_env_example_floris(cuda_device):
+    """examples/example_floris.py: Dec_Ablaincourt_Floris, StepPercentage, load_coef=1, AEC loop until all agents done."""
+    from wfcrl_b200 import environments as envs
+    from wfcrl_b200.rewards import StepPercentage
+
+    env = envs.make("Dec_Ablaincourt_Floris", max_num_steps=30, reward_shaper=StepPercentage(), load_coef=1)
+    lx, ly = layout("Ablaincourt_")
+    ref = env_oracle.MAEnvOracle(lx, ly, solver=c_oracle.solve, max_num_steps=30, load_coef=1,
+                                 reward_shaper=env_oracle.StepPercentage())
+
+    def policy(agent, i):
+        if agent == "turbine_1" and i == 20:
+            return {"yaw": np.array([15.0])}
+        if i % 3 == 0:
+            return {"yaw": np.array([-4.0])}
+        return {"yaw": np.array([0.0])}
+
+    def run(e):
+        e.reset(options={"wind_speed": 9.0, "wind_direction": 268.0})
+        r = {a: 0 for a in e.possible_agents}
+        done = {a: False for a in e.possible_agents}
+        n = {a: 0 for a in e.possible_agents}
+        for agent in e.agent_iter():
+            obs, reward, term, trunc, info = e.last()
+            done[agent] = done[agent] or term or trunc
+            r[agent] += reward
+            if done[agent]:
+                action = None
+            else:
+                action = policy(agent, n[agent])
+                n[agent] += 1
+            e.step(action)
+        return r, n
+
+    r, n = run(env)
+    rr, rn = run(ref)
+    assert n == rn and all(v == 29 for v in n.values())
+    for a in r:
+        assert abs(float(np.asarray(r[a]).reshape(-1)[0]) - float(np.asarray(rr[a]).reshape(-1)[0])) < 1e-7
+    assert set(env.history["turbine_1"].keys()) == {"observation", "reward", "load", "power"}
+    assert len(env.history["turbine_3"]["power"]) > 0
+
+
+def test_control_validation_errors(cuda_device):
+    from wfcrl_b200 import environments as envs
+
+    with pytest.raises(ValueError):
+        envs.make("Ablaincourt_Floris", controls={"pitch": (0, 45, 1)})
+    with pytest.raises(ValueError):
+        envs.make("Ablaincourt_Floris", controls={"yaw": (20, -20, 1)})
+    with pytest.raises(ValueError):
+        envs.make("NoSuchFarm_Floris")
+    with pytest.warns(UserWarning):
+        env = envs.make("Turb3_Row1_Floris", controls={"yaw": (-20, 20)}, log=False)
+    assert env.controls["yaw"] == (-20, 20, 1)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_make_vec_matches_oracle_with_autoreset(cuda_device, precision):
+    import torch
+
+    from wfcrl_b200 import environments as envs
+
+    B, steps, max_steps = 6, 9, 6
+    env = envs.make_vec("Turb6_Row2_Floris", B, precision=precision, max_num_steps=max_steps, exact_host_trig=True)
+    obs = env.reset(seed=100)
+    lx, ly = layout("Turb6_Row2_")
+    refs = [env_oracle.EnvOracle(lx, ly, solver=c_oracle.solve, max_num_steps=max_steps) for _ in range(B)]
+    robs = [r.reset(seed=100 + b) for b, r in enumerate(refs)]
+    tol = 1e-9 if precision == "f64" else 1e-4
+    fw = obs["freewind_measurements"].double().cpu().numpy()
+    for b in range(B):
+        assert np.allclose(fw[b], robs[b]["freewind_measurements"], rtol=1e-7 if precision == "f32" else 0, atol=0)
+    rng = np.random.default_rng(0)
+    n_trunc = 0
+    for k in range(steps):
+        a = rng.uniform(-5, 5, (B, 6)).astype(np.float32)
+        obs, reward, term, trunc, info = env.step(torch.as_tensor(a, device="cuda"))
+        rew = reward.double().cpu().numpy()
+        tr = trunc.cpu().numpy()
+        assert not term.any()
+        if k < max_steps - 1:
+            for b, r in enumerate(refs):
+                o, rr, _t, rtr, _i = r.step({"yaw": a[b].copy()})
+                assert abs(rew[b] - rr[0]) <= tol * max(1, abs(rr[0]))
+                assert bool(tr[b]) == bool(rtr)
+                if not rtr:
+                    assert np.array_equal(obs["yaw"][b].cpu().numpy().astype(np.float32), o["yaw"])
+        if tr.any():
+            n_trunc += 1
+            assert tr.all() and "final_observation" in info
+            # auto-reset: yaw back to zero, a fresh episode has started
+            assert float(obs["yaw"].abs().max()) == 0.0
+    assert n_trunc == 1
+    stats = env.episode_statistics()
+    assert stats["episodes"] == B and stats["length_mean"] == max_steps - 1
+    env.close()
+
+
+def test_make_vec_decentralized_and_time_series(cuda_device):
+    import torch
+
+    from wfcrl_b200 import environments as envs
+
+    B = 3
+    env = envs.make_vec("Dec_Ablaincourt_Floris", B, precision="f64", max_num_steps=10)
+    obs = env.reset(options={"wind_speed": 8.0, "wind_direction": 270.0})
+    assert set(obs.keys()) == set(env.possible_agents) and set(obs["turbine_1"].keys()) == {"yaw", "wind_speed", "wind_direction"}
+    acts = {a: {"yaw": torch.full((B,), 5.0)} for a in env.possible_agents}
+    for _ in range(3):
+        obs, rew, term, trunc, info = env.step(acts)
+    # stale accumulator for non-last agents: 5, 10, 15 ; last agent: 5, 5, 10 (see test_env_oracle)
+    assert float(obs["turbine_1"]["yaw"][0]) == 15.0 and float(obs["turbine_7"]["yaw"][0]) == 10.0
+    assert rew["turbine_1"].shape == (B,) and info["turbine_2"]["load"].shape == (B, 4)
+    env.close()
+    # wind time series: wind changes before every solve; reward normalised with the PREVIOUS state's speed
+    series = np.array([[8.0, 270.0], [9.0, 265.0], [7.0, 275.0]])
+    env = envs.make_vec("Turb3_Row1_Floris", 2, precision="f64", max_num_steps=10, wind_time_series=series)
+    np.random.seed(0)
+    env.reset()
+    lx, ly = layout("Turb3_Row1_")
+    pos = env._series_pos.cpu().numpy().copy()
+    prev_ws = series[pos, 0]
+    for k in range(4):
+        obs, reward, term, trunc, info = env.step(torch.zeros(2, 3))
+        pos = (pos + 1) % 3
+        for b in range(2):
+            sol = c_oracle.solve(lx, ly, series[pos[b], 0], series[pos[b], 1], np.zeros(3))
+            expect = np.mean(sol.power_W / 1e6 * 1e3 / prev_ws[b] ** 3) - 0.1 * np.mean(
+                np.abs(np.stack([sol.ti, sol.std_u, sol.std_v, sol.std_w], 1)))
+            assert abs(float(reward[b]) - expect) < 1e-9 * abs(expect)
+            assert abs(float(obs["freewind_measurements"][b, 0]) - series[pos[b], 0]) < 1e-12
+        prev_ws = series[pos, 0]
+    env.close()
+
+
+def test_sharded_batches_equal_single_batch(cuda_device):
+    """env ids are global, so a batch split into shards gives identical per-env trajectories."""
+    import torch
+
+    from wfcrl_b200 import environments as envs
+    from wfcrl_b200.dist import shard_range
+
+    B, T = 10, 16
+    full = envs.make_vec("Turb16_Row5_Floris", B, precision="f32", max_num_steps=20)
+    full.reset(seed=7)
+    shards = []
+    for r in range(3):
+        lo, hi = shard_range(B, r, 3)
+        e = envs.make_vec("Turb16_Row5_Floris", hi - lo, precision="f32", max_num_steps=20, env_id_offset=lo)
+        e.reset(seed=7)
+        shards.append((lo, hi, e))
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1)
+    for _ in range(5):
+        a = torch.rand(B, T, device="cuda", generator=gen) * 10 - 5
+        obs, rew, *_ = full.step(a)
+        for lo, hi, e in shards:
+            o2, r2, *_ = e.step(a[lo:hi].contiguous())
+            assert torch.equal(r2, rew[lo:hi]) and torch.equal(o2["wind_speed"], obs["wind_speed"][lo:hi])
+    full.close()
+    for *_x, e in shards:
+        e.close()

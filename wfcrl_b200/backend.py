@@ -165,9 +165,21 @@ class FlorisBatch:
         assert ti.dtype == torch.float64 and ti.is_cuda and ti.shape == (self.B,)
         _lib.check(self.lib.wf_set_turbulence_intensity(self.handle, _ptr(ti), self._stream()))
 
-    def update_wind(self, wind_speed: torch.Tensor, wind_direction: torch.Tensor):
+    def update_wind(self, wind_speed: torch.Tensor, wind_direction: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                    host_trig: bool = False):
+        """FlorisInterface.update_wind for every (or the masked) env: new free-stream wind, counters untouched.
+        ``host_trig=True`` computes cosd/sind of the deviation with numpy (one host round trip) for bit-exact geometry."""
         assert wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64
-        _lib.check(self.lib.wf_update_wind(self.handle, None, _ptr(wind_speed), _ptr(wind_direction), self._stream()))
+        cs = None
+        if host_trig:
+            wd = wind_direction.detach().cpu().numpy()
+            dev = (((wd % 360.0) - 270.0) % 360.0 + 360.0) % 360.0
+            cs = torch.as_tensor(np.stack([np.cos(np.radians(dev)), np.sin(np.radians(dev))], 1), device=self.device)
+            cs = cs.contiguous()
+        _lib.check(self.lib.wf_update_wind(self.handle, _ptr(mask), _ptr(wind_speed), _ptr(wind_direction), _ptr(cs),
+                                           self._stream()))
+        if cs is not None:
+            torch.cuda.current_stream(self.device).synchronize()
 
     # ------------------------------------------------------------------------------------------------------
     def _shape(self, kind):

@@ -436,16 +436,14 @@ int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_
     return WF_OK;
 }
 
-int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, void* stream) {
+int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, const double* d_cs,
+                   void* stream) {
     if (!h || !d_ws || !d_wd) return set_err(WF_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t B = h->model.B;
-    if (d_mask) return set_err(WF_ERR_INVALID, "masked wf_update_wind is not implemented yet");
-    CUDA_TRY(cudaMemcpyAsync(h->st.ws, d_ws, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(h->st.wd, d_wd, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(wf_launch_geometry(h->model, h->st, nullptr, nullptr, st));
-    h->launches += 1;
+    CUDA_TRY(wf_launch_set_wind(h->model, h->st, d_mask, d_ws, d_wd, st));
+    CUDA_TRY(wf_launch_geometry(h->model, h->st, d_mask, d_cs, st));
+    h->launches += 2;
     return WF_OK;
 }
 

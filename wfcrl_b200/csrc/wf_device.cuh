@@ -97,6 +97,8 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
                                  cudaStream_t stream);
+cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
+                               const double* d_wd, cudaStream_t stream);
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                   const double* d_wd, cudaStream_t stream);
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);

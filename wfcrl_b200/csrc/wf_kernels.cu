@@ -229,6 +229,15 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
     }
 }
 
+// FlorisInterface.update_wind for masked envs: new free-stream wind, counters untouched (interface.py:663-671)
+__global__ void wf_set_wind_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
+                                   const double* __restrict__ ws, const double* __restrict__ wd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.B || (mask && !mask[b])) return;
+    s.ws[b] = ws[b];
+    s.wd[b] = fmod_py(wd[b], 360.0);
+}
+
 // reset per-env scalars/accumulators for masked envs
 __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
                                       const double* __restrict__ ws, const double* __restrict__ wd) {
@@ -676,6 +685,12 @@ static inline int round_up_warp(int n) { return (n + 31) / 32 * 32; }
 cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_cs_override,
                                cudaStream_t stream) {
     wf_geometry_kernel<<<m.B, round_up_warp(m.T), 0, stream>>>(m, s, d_mask, d_cs_override);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
+                               const double* d_wd, cudaStream_t stream) {
+    wf_set_wind_kernel<<<(m.B + 127) / 128, 128, 0, stream>>>(m, s, d_mask, d_ws, d_wd);
     return cudaGetLastError();
 }
 

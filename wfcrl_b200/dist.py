@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: the env batch is sharded across ranks (one process per GPU); the step has NO collective.
+``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in CPU tests) is used only to all-gather per-rank
+episode statistics at report time (BASELINE.json north_star)."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_envs_global: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous global env-id range [lo, hi) owned by ``rank``; earlier ranks take the remainder."""
+    base, rem = divmod(int(num_envs_global), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def gather_episode_stats(returns: torch.Tensor, lengths: torch.Tensor) -> Dict[str, float]:
+    """All-gather (sum, sum of squares, count, length sum) of finished-episode returns across ranks and reduce them to
+    global statistics.  ``returns``/``lengths``: 1-D tensors of this rank's finished episodes (may be empty)."""
+    r = returns.double()
+    local = torch.stack([r.sum(), (r * r).sum(), torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device),
+                         lengths.double().sum()])
+    rank, size = world()
+    if size > 1:
+        parts = [torch.zeros_like(local) for _ in range(size)]
+        dist.all_gather(parts, local)
+        total = torch.stack(parts).sum(0)
+    else:
+        total = local
+    s, ss, n, ln = (float(v) for v in total)
+    mean = s / n if n else float("nan")
+    var = max(ss / n - mean * mean, 0.0) if n else float("nan")
+    return {"episodes": n, "return_mean": mean, "return_std": var ** 0.5 if n else float("nan"),
+            "length_mean": ln / n if n else float("nan"), "world_size": size}

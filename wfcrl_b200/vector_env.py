@@ -1,0 +1,238 @@
+"""Batched vector environments: thousands of independent ``*_Floris`` envs stepped by ONE kernel launch.
+
+``VecWindFarmEnv`` keeps the reference's Gymnasium step/reset contract (wfcrl/simple_env.py:49-96) with a leading
+batch dimension and torch CUDA tensors instead of numpy arrays:
+
+    obs = env.reset(seed=..)                         # dict: yaw, freewind_measurements, wind_speed, wind_direction
+    obs, reward, terminated, truncated, info = env.step(action)     # action: float32 [B, T] (or {"yaw": ...})
+
+Everything between action and observation -- actuation constraint, float32 yaw transition, FLORIS GCH wake solve,
+measures, reward + shaper, truncation -- runs inside the fused sm_100a step kernel (``FlorisBatch.step``).
+``VecMAWindFarmEnv`` is the decentralised flavour (one agent per turbine, PettingZoo parallel-API style: one call = one
+full agent cycle of the reference's AEC env, wfcrl/multiagent_env.py:159-254).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from . import spaces
+from .backend import FlorisBatch
+from .layouts import get_layout
+from .rewards import DoNothingReward, RewardShaper
+
+_OBS_BOUNDS = {"wind_speed": (3.0, 28.0), "wind_direction": (0.0, 360.0)}
+
+
+class VecWindFarmEnv:
+    metadata = {"name": "vectorized-windfarm"}
+
+    def __init__(self, layout: Union[str, Dict], num_envs: int, *, device: int = 0, precision: str = "f32",
+                 kernel: Optional[str] = None, controls: Optional[dict] = None, continuous_control: bool = True,
+                 reward_shaper: Optional[RewardShaper] = None, max_num_steps: int = 500, load_coef: float = 0.1,
+                 start_iter: int = 0, auto_reset: bool = True, multi_agent: bool = False, env_id_offset: int = 0,
+                 wind_time_series: Optional[np.ndarray] = None, exact_host_trig: Optional[bool] = None):
+        case = get_layout(layout) if isinstance(layout, str) else layout
+        self.farm_case = case
+        self.num_envs = int(num_envs)
+        self.num_turbines = case["num_turbines"]
+        self.dt = case.get("dt", 60)
+        controls = dict(controls or {"yaw": (-40, 40, 5)})
+        if set(controls) != {"yaw"}:
+            raise ValueError(f"Cannot control {sorted(set(controls) - {'yaw'})}. Interface FlorisInterface only allows "
+                             "for the following: ['yaw']")
+        lo, hi, *rest = controls["yaw"]
+        if not lo < hi:
+            raise ValueError("Wrong bounds for actuator yaw: ensure that lower_bound < upper_bound")
+        step = rest[0] if rest else 1
+        self.controls = {"yaw": (lo, hi, step)}
+        self.continuous_control = continuous_control
+        self.max_num_steps = max_num_steps
+        self.start_iter = start_iter
+        self.load_coef = load_coef
+        self.auto_reset = auto_reset
+        self.env_id_offset = int(env_id_offset)
+        self.reward_shaper = reward_shaper if reward_shaper is not None else DoNothingReward()
+        code = getattr(self.reward_shaper, "kernel_code", None)
+        if code is None:
+            raise ValueError("the batched path supports DoNothingReward, ReferencePercentage and StepPercentage")
+        precision = {"fp32": "f32", "fp64": "f64"}.get(precision, precision)
+        kernel = kernel or ("fast" if precision == "f32" else "basic")
+        self.precision = precision
+        self.exact_host_trig = (precision == "f64") if exact_host_trig is None else exact_host_trig
+        self.backend = FlorisBatch(case["xcoords"], case["ycoords"], self.num_envs, device=device, precision=precision,
+                                   kernel=kernel, max_iter=start_iter + max_num_steps, yaw_bounds=(lo, hi, step),
+                                   load_coef=load_coef, reward_shaper=code,
+                                   shaper_reference=float(getattr(self.reward_shaper, "reference", 0.0)),
+                                   continuous_control=continuous_control, multi_agent=multi_agent)
+        self.device = self.backend.device
+        T = self.num_turbines
+        self.single_action_space = spaces.Dict({"yaw": spaces.Box(-step, step, shape=(T,))}) if continuous_control \
+            else spaces.Dict({"yaw": spaces.MultiDiscrete([3] * T)})
+        ones = np.ones(T, dtype=np.float32)
+        self.single_observation_space = spaces.Dict(OrderedDict([
+            ("yaw", spaces.Box(ones * lo, ones * hi, shape=(T,))),
+            ("freewind_measurements", spaces.Box(np.array([3, 0], np.float32), np.array([28, 360], np.float32), shape=(2,))),
+            ("wind_speed", spaces.Box(ones * 3, ones * 28, shape=(T,))),
+            ("wind_direction", spaces.Box(ones * 0, ones * 360, shape=(T,))),
+        ]))
+        self.action_space = self.single_action_space
+        self.observation_space = self.single_observation_space
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(0x5EED + self.env_id_offset)
+        self._iters = np.zeros(self.num_envs, dtype=np.int64)  # host mirror of FlorisInterface._num_iter
+        self._series = None
+        if wind_time_series is not None:
+            series = np.asarray(wind_time_series, dtype=np.float64)
+            assert series.ndim == 2 and series.shape[1] >= 2, "time series rows are [speed, direction]"
+            self._series = torch.as_tensor(series[:, :2], device=self.device)
+            self._series_pos = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
+        self._zeros_bool = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.episode_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
+        self.finished_returns, self.finished_lengths = [], []
+        self._needs_reset = True
+
+    # -- wind sampling ------------------------------------------------------------------------------------------
+    def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray):
+        """The reference's reset distribution with numpy's Generator, one stream per GLOBAL env id
+        (wfcrl/mdp.py:235-258): bit-identical to what ``WindFarmMDP.reset(seed + env_id)`` would draw."""
+        ws = np.empty(len(env_ids))
+        wd = np.empty(len(env_ids))
+        for k, b in enumerate(env_ids):
+            rng = np.random.default_rng(None if seed is None else seed + self.env_id_offset + int(b))
+            ws[k] = np.clip(8 * rng.weibull(8), 3, 28)
+            wd[k] = np.clip(rng.normal(270, 20) % 360, 0, 360)
+        return ws, wd
+
+    def sample_wind_device(self):
+        """Same distribution drawn on the device (Philox), used for in-loop auto-resets (no host round trip)."""
+        B = self.num_envs
+        u = torch.rand(B, dtype=torch.float64, device=self.device, generator=self._gen)
+        ws = (8.0 * (-torch.log1p(-u)).pow(1.0 / 8.0)).clamp_(3.0, 28.0)
+        wd = torch.remainder(270.0 + 20.0 * torch.randn(B, dtype=torch.float64, device=self.device,
+                                                        generator=self._gen), 360.0).clamp_(0.0, 360.0)
+        return ws, wd
+
+    # -- API ------------------------------------------------------------------------------------------------------
+    def _obs(self, out):
+        return OrderedDict([("yaw", out["yaw"]), ("freewind_measurements", out["freewind"]),
+                            ("wind_speed", out["wind_speed"]), ("wind_direction", out["wind_direction"])])
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None, env_ids=None):
+        """Reset all (or ``env_ids``) envs.  ``options`` may carry ``wind_speed`` / ``wind_direction`` (scalars or
+        per-env arrays) exactly like the reference; otherwise both are sampled per env."""
+        ids = np.arange(self.num_envs) if env_ids is None else np.asarray(env_ids)
+        options = options or {}
+        ws_s, wd_s = self.sample_wind_host(seed, ids)
+        ws = np.broadcast_to(np.asarray(options.get("wind_speed", ws_s), dtype=np.float64), ids.shape)
+        wd = np.broadcast_to(np.asarray(options.get("wind_direction", wd_s), dtype=np.float64), ids.shape)
+        if self._series is not None:
+            start = np.random.randint(0, self._series.shape[0], size=len(ids))  # interface.py:517
+            self._series_pos[torch.as_tensor(ids, device=self.device)] = torch.as_tensor(start, device=self.device)
+            first = self._series[self._series_pos[torch.as_tensor(ids, device=self.device)]].cpu().numpy()
+            ws, wd = first[:, 0], first[:, 1]
+        out = self.backend.reset(ws, wd, env_ids=ids.astype(np.int32), host_trig=self.exact_host_trig,
+                                 warmup_solves=self.start_iter + 1)
+        self._iters[ids] = self.start_iter + 1
+        idt = torch.as_tensor(ids, device=self.device)
+        self.episode_returns[idt] = 0
+        self.episode_lengths[idt] = 0
+        self._needs_reset = False
+        return self._obs(out)
+
+    def step(self, action):
+        assert not self._needs_reset, "Call reset before `step`"
+        if isinstance(action, dict):
+            action = action["yaw"]
+        if not torch.is_tensor(action):
+            action = torch.as_tensor(np.asarray(action, dtype=np.float32), device=self.device)
+        action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        if self._series is not None:  # time-series mode: the wind moves before every solve (interface.py:563)
+            self._series_pos = (self._series_pos + 1) % self._series.shape[0]
+            row = self._series[self._series_pos]
+            self.backend.update_wind(row[:, 0].contiguous(), row[:, 1].contiguous(), host_trig=self.exact_host_trig)
+        out = self.backend.step(action)
+        self._iters += 1
+        reward = out["reward"]
+        truncated = out["truncated"].bool()
+        self.episode_returns += reward.double()
+        self.episode_lengths += 1
+        info = {"power": out["power"], "load": out["load"]}
+        obs = self._obs(out)
+        done_host = self._iters >= self.start_iter + self.max_num_steps
+        if done_host.any():
+            mask = out["truncated"]
+            self.finished_returns.append(self.episode_returns[truncated].clone())
+            self.finished_lengths.append(self.episode_lengths[truncated].clone())
+            if self.auto_reset:
+                # same-step autoreset: final observation is preserved in info, obs rows of finished envs restart
+                info["final_observation"] = OrderedDict((k, v.clone()) for k, v in obs.items())
+                info["final_info"] = {"power": out["power"].clone(), "load": out["load"].clone()}
+                truncated = truncated.clone()
+                reward = reward.clone()
+                ws, wd = self.sample_wind_device()
+                out = self.backend.reset_masked(mask.clone(), ws, wd, warmup_solves=self.start_iter + 1)
+                obs = self._obs(out)
+                self.episode_returns[truncated] = 0
+                self.episode_lengths[truncated] = 0
+                self._iters[done_host] = self.start_iter + 1
+        return obs, reward, self._zeros_bool, truncated, info
+
+    def episode_statistics(self):
+        """Global statistics of the finished episodes (all-gathered over ranks when torch.distributed is initialised)."""
+        from .dist import gather_episode_stats
+
+        if self.finished_returns:
+            r, ln = torch.cat(self.finished_returns), torch.cat(self.finished_lengths)
+        else:
+            r = torch.zeros(0, dtype=torch.float64, device=self.device)
+            ln = torch.zeros(0, dtype=torch.long, device=self.device)
+        return gather_episode_stats(r, ln)
+
+    def close(self):
+        self.backend.close()
+
+
+class VecMAWindFarmEnv(VecWindFarmEnv):
+    """Decentralised batch: agents ``turbine_1..T``; ``step`` takes the actions of ALL agents (a full AEC cycle) either
+    as a float32 [B, T] tensor (column k = agent k) or as ``{agent: {"yaw": tensor[B]}}``, and returns per-agent dicts."""
+
+    metadata = {"name": "vectorized-multiagent-windfarm", "is_parallelizable": True}
+
+    def __init__(self, layout, num_envs, **kwargs):
+        kwargs["multi_agent"] = True
+        super().__init__(layout, num_envs, **kwargs)
+        self.possible_agents = [f"turbine_{k + 1}" for k in range(self.num_turbines)]
+        self.agents = self.possible_agents[:]
+        self.agent_name_mapping = {a: k for k, a in enumerate(self.possible_agents)}
+        lo, hi, step = self.controls["yaw"]
+        self._obs_spaces = {a: {"yaw": spaces.Box(lo, hi), "wind_speed": spaces.Box(3, 28),
+                                "wind_direction": spaces.Box(0, 360)} for a in self.possible_agents}
+        self._act_spaces = {a: {"yaw": spaces.Box(-step, step)} for a in self.possible_agents}
+
+    def observation_space(self, agent):
+        return self._obs_spaces[agent]
+
+    def action_space(self, agent):  # noqa: D102 - shadows the attribute of the centralised env on purpose
+        return self._act_spaces[agent]
+
+    def _split(self, obs):
+        return {a: OrderedDict((k, v[:, i]) for k, v in obs.items() if k != "freewind_measurements")
+                for a, i in self.agent_name_mapping.items()}
+
+    def reset(self, seed=None, options=None, env_ids=None):
+        return self._split(super().reset(seed, options, env_ids))
+
+    def step(self, actions):
+        if isinstance(actions, dict) and actions and next(iter(actions)) in self.agent_name_mapping:
+            cols = [torch.as_tensor(actions[a]["yaw"], device=self.device).reshape(self.num_envs) for a in self.possible_agents]
+            actions = torch.stack(cols, 1)
+        obs, reward, terminated, truncated, info = super().step(actions)
+        per_agent_info = {a: {"power": info["power"][:, i], "load": info["load"][:, i]}
+                          for a, i in self.agent_name_mapping.items()}
+        return (self._split(obs), {a: reward for a in self.possible_agents}, {a: terminated for a in self.possible_agents},
+                {a: truncated for a in self.possible_agents}, per_agent_info)
