@@ -149,6 +149,13 @@ int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, voi
  */
 int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* h_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
+/*
+ * Host-buffer flavour of wf_update_command: the one call a reference-side binding needs to replace
+ * FlorisInterface.update_command (interface.py:557-586) without managing device memory.
+ * h_yaw: HOST double [B][T] absolute yaw command or NULL (keep the current command).  Synchronous.
+ */
+int wf_update_command_host(WfHandle h, const double* h_yaw, const WfHostOut* h_out);
+
 /* Change per-env wind without resetting counters (FlorisInterface.update_wind, interface.py:663-671; time-series
  * mode, interface.py:503-524,563).  Rebuilds the rotated/sorted geometry of the selected envs.
  *   d_mask: uint8 [B] or NULL (= all) ; d_ws, d_wd: double [B] (read where selected; wd is reduced % 360)

@@ -56,6 +56,7 @@ SYMBOLS = {
     "wf_step": (C.c_int, [_P, _P, C.POINTER(WfStepOut), _P]),
     "wf_update_command": (C.c_int, [_P, _P, C.POINTER(WfStepOut), _P]),
     "wf_step_host": (C.c_int, [_P, _P, C.POINTER(WfStepOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "wf_update_command_host": (C.c_int, [_P, _P, C.POINTER(WfStepOut)]),
     "wf_update_wind": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "wf_set_turbulence_intensity": (C.c_int, [_P, _P, _P]),
     "wf_get_state": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),

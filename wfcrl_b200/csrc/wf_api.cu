@@ -39,6 +39,7 @@ struct WfHandle_t {
     double *h_rws = nullptr, *h_rwd = nullptr, *h_rcs = nullptr;
     // staging for wf_step_host
     float* d_action = nullptr;
+    double* d_yaw_cmd = nullptr;
     WfOutPtrs d_out = {};
     cudaStream_t host_stream = nullptr;
     uint64_t launches = 0;
@@ -392,12 +393,14 @@ int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, voi
     return launch_step(h, WF_MODE_INTERFACE, nullptr, nullptr, d_yaw, to_ptrs(out), (cudaStream_t)stream);
 }
 
-int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_t* h2d, uint64_t* d2h) {
-    if (!h || !h_action || !ho) return set_err(WF_ERR_INVALID, "NULL argument");
+// shared implementation of the two host-buffer entry points
+static int step_host_impl(WfHandle h, int mode, const float* h_action, const double* h_yaw, const WfHostOut* ho,
+                          uint64_t* h2d, uint64_t* d2h) {
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t B = h->model.B, T = h->model.T, BT = B * T, es = h->es;
     if (!h->d_action) {
         TRY(dev_alloc(h, &h->d_action, BT));
+        TRY(dev_alloc(h, &h->d_yaw_cmd, BT));
         char* p;
         TRY(dev_alloc(h, &p, BT * es)); h->d_out.yaw = p;
         TRY(dev_alloc(h, &p, BT * es)); h->d_out.wind_speed = p;
@@ -410,8 +413,14 @@ int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_
     }
     cudaStream_t st = h->host_stream;
     uint64_t up = 0, down = 0;
-    CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, sizeof(float) * BT, cudaMemcpyHostToDevice, st));
-    up += sizeof(float) * BT;
+    if (h_action) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, sizeof(float) * BT, cudaMemcpyHostToDevice, st));
+        up += sizeof(float) * BT;
+    }
+    if (h_yaw) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd, h_yaw, sizeof(double) * BT, cudaMemcpyHostToDevice, st));
+        up += sizeof(double) * BT;
+    }
     WfOutPtrs o = {};
     if (ho->yaw) o.yaw = h->d_out.yaw;
     if (ho->wind_speed) o.wind_speed = h->d_out.wind_speed;
@@ -421,7 +430,7 @@ int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_
     if (ho->reward) o.reward = h->d_out.reward;
     if (ho->freewind) o.freewind = h->d_out.freewind;
     if (ho->truncated) o.truncated = h->d_out.truncated;
-    TRY(launch_step(h, WF_MODE_ENV, nullptr, h->d_action, nullptr, o, st));
+    TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st));
 #define D2H(field, bytes)                                                                              \
     if (ho->field) {                                                                                   \
         CUDA_TRY(cudaMemcpyAsync(ho->field, h->d_out.field, (bytes), cudaMemcpyDeviceToHost, st));      \
@@ -434,6 +443,18 @@ int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_
     if (h2d) *h2d = up;
     if (d2h) *d2h = down;
     return WF_OK;
+}
+
+int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_t* h2d, uint64_t* d2h) {
+    if (!h || !h_action || !ho) return set_err(WF_ERR_INVALID, "NULL argument");
+    return step_host_impl(h, WF_MODE_ENV, h_action, nullptr, ho, h2d, d2h);
+}
+
+int wf_update_command_host(WfHandle h, const double* h_yaw, const WfHostOut* ho) {
+    if (!h || !ho) return set_err(WF_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());  // order after resets / wind updates issued on other streams
+    return step_host_impl(h, WF_MODE_INTERFACE, nullptr, h_yaw, ho, nullptr, nullptr);
 }
 
 int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const double* d_wd, const double* d_cs,
