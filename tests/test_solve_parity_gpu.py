@@ -72,3 +72,28 @@ def test_solve_matches_numpy_oracle_and_golden(cuda_device):
     assert np.max(np.abs(ws_l - np.array(kat["local_wind_speed"]))) < 2e-8
     assert np.max(np.abs(wd_l - np.array(kat["local_wind_direction"]))) < 2e-8
     fb.close()
+
+
+def test_generic_fast_kernel_matches_specialised(cuda_device, monkeypatch):
+    """The tuned kernel exists in two instantiations: model constants baked in as immediates (default model) and read
+    from kernel parameters / shared memory (any other model).  Both must give the same results (bitwise)."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb_TCRWP_")
+    B, T = 16, len(lx)
+    ws, wd = sample_winds(B, 4)
+    yaw = torch.as_tensor(np.random.default_rng(0).uniform(-30, 30, (B, T)), device="cuda")
+    outs = []
+    for forced in (False, True):
+        if forced:
+            monkeypatch.setenv("WFCRL_B200_NO_BAKED", "1")
+        fb = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=10)
+        fb.reset(ws, wd, warmup_solves=0)
+        out = fb.update_command(yaw)
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in out.items()})
+        fb.close()
+    for k in ("power", "wind_speed", "wind_direction", "load"):
+        assert torch.allclose(outs[0][k], outs[1][k], rtol=2e-6, atol=1e-6), k

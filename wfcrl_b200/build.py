@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwfcrl_b200.so")
 SOURCES = ["wf_api.cu", "wf_kernels.cu", "wf_fast.cu"]
-HEADERS = ["wf_device.cuh", os.path.join("..", "..", "include", "wfcrl_b200.h")]
+HEADERS = ["wf_device.cuh", "wf_host_const.h", "gen_baked.cu", os.path.join("..", "..", "include", "wfcrl_b200.h")]
+BAKED = os.path.join(CSRC, "wf_fast_baked.inc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--resource-usage",
@@ -38,6 +39,14 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    # step 1: bake the default model's kernel constants into a header (host program built and run at build time)
+    gen_exe = os.path.join(HERE, "_gen_baked")
+    subprocess.run([_nvcc(), "-O1", "-std=c++17", "-o", gen_exe, os.path.join(CSRC, "gen_baked.cu")], check=True,
+                   capture_output=True, text=True)
+    with open(BAKED, "w") as fp:
+        fp.write(subprocess.run([gen_exe], check=True, capture_output=True, text=True).stdout)
+    os.remove(gen_exe)
+    # step 2: the library
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr

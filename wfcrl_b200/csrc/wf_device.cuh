@@ -60,6 +60,7 @@ struct WfFastConst {
     float zz[6][3];        // Z_k + c_v + NUM_EPS, vortices in FLORIS order V1..V6 (see wf_kernels.cu transverse())
     float zz2[6][3];       // zz^2
     float ez[6][3];        // exp(-zz^2 / eps^2)
+    float cblk[48];        // the same constants packed for the kernel's shared-memory block (see build_fast_const)
     float a_top, a_bot, a_core;   // secondary steering: mean over the own grid of z/(2 pi r) * core per unit circulation
     float cv[3][9], cw[3][9];     // self-induced V / W per unit (Gt, Gb, Gwr) on the own grid
     float sv[3];                  // sum over the 9 points of cv
@@ -102,8 +103,8 @@ cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                   const double* d_wd, cudaStream_t stream);
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);
-cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
+cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                 const WfOutPtrs& out, cudaStream_t stream);
-cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);

@@ -18,8 +18,13 @@
 // Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
 // wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
 #include "wf_device.cuh"
+#include "wf_fast_baked.inc"
 
 namespace {
+
+// model constant `name`: a compile-time literal in the specialised (BAKED) instantiation, a kernel parameter otherwise
+#define KC(name) (BAKED ? WfBaked::name : fc.name)
+
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -59,10 +64,11 @@ struct SmemView {
     float *ynew;              // [T] new yaw, degrees, ORIGINAL order
     uchar4* idx;              // [T]
     unsigned char* ordr;      // [T]
+    float4* cblk;             // [12] per-model vortex constants, 4 float4 per vertical index k (LDS.128 broadcast)
 };
 
 __host__ __device__ inline size_t fast_smem_bytes(int T) {
-    size_t n = 0;
+    size_t n = 12 * 16;          // cblk
     n += (size_t)3 * 9 * T * 4;  // wsq, v, w
     n += (size_t)2 * T * 8;      // xhl, yhl
     n += (size_t)3 * T * 4;      // tia
@@ -74,7 +80,8 @@ __host__ __device__ inline size_t fast_smem_bytes(int T) {
 
 __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
     SmemView s;
-    float2* f2 = (float2*)base;
+    s.cblk = (float4*)base;
+    float2* f2 = (float2*)(base + 12 * 16);
     s.xhl = f2;
     s.yhl = f2 + T;
     float* f = (float*)(f2 + 2 * T);
@@ -92,6 +99,7 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
     return s;
 }
 
+template <bool BAKED>
 __global__ void __launch_bounds__(32, 16)
 wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfFastConst fc, const WfState s,
                     const uint8_t* __restrict__ mask, const float* __restrict__ action,
@@ -135,6 +143,7 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         sm.idx[tt] = s.idx[row + tt];
         sm.ordr[tt] = (unsigned char)s.order[row + tt];
     }
+    if (lane < 12) sm.cblk[lane] = make_float4(fc.cblk[4 * lane], fc.cblk[4 * lane + 1], fc.cblk[4 * lane + 2], fc.cblk[4 * lane + 3]);
     for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.f; sm.v[q] = 0.f; sm.w[q] = 0.f; }
     for (int q = lane; q < 3 * T; q += 32) sm.tia[q] = 0.f;
     __syncwarp();
@@ -153,28 +162,44 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
     const float I02 = I0 * I0;
     const float I0p = __powf(I0, fc.ch_init);
     const float U0a = ws * fc.ratio[0], U0b = ws * fc.ratio[1], U0c = ws * fc.ratio[2];
-    const float D = fc.D;
+    const float D = KC(D);
     __syncwarp();
 
     // lane -> (turbine slot g in the pass, lateral column j); each lane owns the 3 vertical points k of its column
     const int g = lane / 3, j = lane - 3 * g;
     const bool lane_ok = lane < 3 * kTurbPerPass;
     const float offj = (j == 0) ? fc.offj[0] : ((j == 1) ? fc.offj[1] : fc.offj[2]);
+    // prologue mapping: lanes 0..8 (mirrored in 16..24) own rotor point pl of the SOURCE turbine
+    const int pl = lane & 15;
+    const bool pv = pl < 9;
+    const int plc = pv ? pl : 0;
+    const float U0p = (plc % 3 == 0) ? U0a : ((plc % 3 == 1) ? U0b : U0c);
+    const float cvl0 = fc.cv[0][plc], cvl1 = fc.cv[1][plc], cvl2 = fc.cv[2][plc];
+    const float cwl0 = fc.cw[0][plc], cwl1 = fc.cw[1][plc], cwl2 = fc.cw[2][plc];
+    const float c_dec = KC(eps2) * KC(inv_2pi);
+    const float c_e = -KC(inv_eps2) * kLog2e;
+    const float c_ek = -(0.5f * kLog2e) * (BAKED ? WfBaked::dz2_0 : fc.dz2[0]);
+    const float eps2 = KC(eps2);
 
     // ---- sequential solver over sources -------------------------------------------------------------
     for (int i = 0; i < T; ++i) {
-        // ===== source prologue: every lane computes the same values =====
-        float wq[9], vq[9], wwq[9];
+        // ===== source prologue =====
+        // rotor sums over the source's 9 points: one point per lane, butterfly over 16-lane halves -> uniform values
+        float su3, sv, sw, vq, wwq;
+        {
+            const float wq = sm.wsq[9 * i + plc];
+            vq = sm.v[9 * i + plc];
+            wwq = sm.w[9 * i + plc];
+            const float u = U0p - fsqrt(wq);
+            su3 = pv ? u * u * u : 0.f;
+            sv = pv ? vq : 0.f;
+            sw = pv ? wwq : 0.f;
 #pragma unroll
-        for (int p = 0; p < 9; ++p) { wq[p] = sm.wsq[9 * i + p]; vq[p] = sm.v[9 * i + p]; wwq[p] = sm.w[9 * i + p]; }
-        float su3 = 0.f, sv = 0.f, sw = 0.f;
-#pragma unroll
-        for (int p = 0; p < 9; ++p) {
-            const float U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
-            const float u = U0k - fsqrt(wq[p]);
-            su3 = fmaf(u * u, u, su3);
-            sv += vq[p];
-            sw += wwq[p];
+            for (int sft = 8; sft > 0; sft >>= 1) {
+                su3 += __shfl_xor_sync(0xffffffffu, su3, sft);
+                sv += __shfl_xor_sync(0xffffffffu, sv, sft);
+                sw += __shfl_xor_sync(0xffffffffu, sw, sft);
+            }
         }
         const float avg = cbrtf(su3 * (1.f / 9.f));
         const float ct_raw = fclamp(interp_f(fc, fc.tab_ct, avg, 0.0001f, 0.9999f), 0.0001f, 0.9999f);
@@ -182,12 +207,12 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         const float ct = ct_raw * cy;
         const float s1c = fsqrt(1.f - ct * cy);
         const float a = 0.5f * frcp(cy) * (1.f - s1c);
-        const float Gtop0 = fc.c_top * ws * ct, Gbot0 = fc.c_bot * ws * ct;
-        const float Gwr = fc.c_wr * (a - a * a) * avg;
+        const float Gtop0 = KC(c_top) * ws * ct, Gbot0 = KC(c_bot) * ws * ct;
+        const float Gwr = KC(c_wr) * (a - a * a) * avg;
         const float Gt = sy * cy * Gtop0, Gb = -(sy * cy * Gbot0);
 
         // A.5 secondary steering through the per-model grid integrals
-        float val = 2.f * (sv * (1.f / 9.f) - Gwr * fc.a_core) * frcp(Gtop0 * fc.a_top - Gbot0 * fc.a_bot);
+        float val = 2.f * (sv * (1.f / 9.f) - Gwr * KC(a_core)) * frcp(Gtop0 * KC(a_top) - Gbot0 * KC(a_bot));
         val = fclamp(val, -1.f, 1.f);
         const float g_rad = -(yr + 0.5f * asinf(val));  // minus the effective yaw, radians
         const float cg = __cosf(g_rad);
@@ -199,8 +224,8 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         const float sy0d = sz0d * cg;
         const float C0 = 1.f - sq1ct;
         const float M0 = C0 * (2.f - C0);
-        const float E0 = C0 * C0 - fc.e3_112 * C0 + fc.e3_13;
-        const float th = fc.dm03 * g_rad * frcp(cg) * (1.f - sqcg);
+        const float E0 = C0 * C0 - KC(e3_112) * C0 + KC(e3_13);
+        const float th = KC(dm03) * g_rad * frcp(cg) * (1.f - sqcg);
         const float sM0 = fsqrt(M0);
         const float tan_th = __sinf(th) * frcp(__cosf(th));
         const float Kc = th * E0 * (1.f / 5.2f) * fsqrt(sy0d * sz0d * frcp(M0));
@@ -208,30 +233,30 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         const float inv_s0d = frcp(sy0d * sz0d);
 
         // TI of the source per lateral column before the yaw-added-recovery update
-        const float tp0 = fsqrt(fmaf(sm.tia[3 * i], sm.tia[3 * i], I02));
-        const float tp1 = fsqrt(fmaf(sm.tia[3 * i + 1], sm.tia[3 * i + 1], I02));
-        const float tp2 = fsqrt(fmaf(sm.tia[3 * i + 2], sm.tia[3 * i + 2], I02));
+        const float ta0 = sm.tia[3 * i], ta1 = sm.tia[3 * i + 1], ta2 = sm.tia[3 * i + 2];
+        const float tp0 = fsqrt(fmaf(ta0, ta0, I02)), tp1 = fsqrt(fmaf(ta1, ta1, I02)), tp2 = fsqrt(fmaf(ta2, ta2, I02));
         const float tpre = (j == 0) ? tp0 : ((j == 1) ? tp1 : tp2);
-        const float beta_term = fc.beta2 * (1.f - sq1ct);
-        const float x0d = D * cg * (1.f + sqcg) * frcp(1.4142135623730951f * fmaf(fc.alpha4, tpre, beta_term));
-        const float kyd = fmaf(fc.ka, tpre, fc.kb);
+        const float beta_term = KC(beta2) * (1.f - sq1ct);
+        const float x0d = D * cg * (1.f + sqcg) * frcp(1.4142135623730951f * fmaf(KC(alpha4), tpre, beta_term));
+        const float kyd = fmaf(KC(ka), tpre, KC(kb));
         const float inv_x0d = frcp(x0d);
         const float delta0 = tan_th * x0d;
         const float Kck = Kc * frcp(kyd);
 
         // own transverse velocities (A.7 on the source's own grid) + yaw-added recovery (in-place TI update)
         const uchar4 ix = sm.idx[i];
-        const bool self_on = (int)ix.x <= i;  // X_i - x_i >= 0
+        const bool self_on = (int)ix.x <= i;  // X_i - x_i >= 0 (warp-uniform)
         float sumV = sv, sumW = sw;
         if (self_on) {
-            sumV += Gt * fc.sv[0] + Gb * fc.sv[1] + Gwr * fc.sv[2];
+            sumV += Gt * (BAKED ? WfBaked::sv0 : fc.sv[0]) + Gb * (BAKED ? WfBaked::sv1 : fc.sv[1]) +
+                    Gwr * (BAKED ? WfBaked::sv2 : fc.sv[2]);
+            const float Vs = Gt * cvl0 + Gb * cvl1 + Gwr * cvl2;
+            const float Ws = fmaxf(Gt * cwl0 + Gb * cwl1 + Gwr * cwl2, 0.f);
+            float rw = pv ? Ws : 0.f;
 #pragma unroll
-            for (int p = 0; p < 9; ++p) {
-                const float Vs = Gt * fc.cv[0][p] + Gb * fc.cv[1][p] + Gwr * fc.cv[2][p];
-                const float Ws = fmaxf(Gt * fc.cw[0][p] + Gb * fc.cw[1][p] + Gwr * fc.cw[2][p], 0.f);
-                sumW += Ws;
-                if (lane == p) { sm.v[9 * i + p] = vq[p] + Vs; sm.w[9 * i + p] = wwq[p] + Ws; }
-            }
+            for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
+            sumW += rw;
+            if (lane < 9) { sm.v[9 * i + lane] = vq + Vs; sm.w[9 * i + lane] = wwq + Ws; }
         }
         const float aI = avg * tp0;
         const float kk2 = 3.f * aI * aI;  // u_term^2 = 2 k = 2 (avg I)^2 / (2/3)
@@ -243,86 +268,88 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         const float tpost = (j == 0) ? tq0 : ((j == 1) ? tq1 : tq2);
 
         // A.8 velocity-model scalars with the updated TI (cos(-yaw) = cy ; sigma_z0 = D / (2 sqrt 2) exactly)
-        const float x0v = D * cy * (1.f + sq1ct) * frcp(1.4142135623730951f * fmaf(fc.alpha4, tpost, beta_term));
-        const float kyv = fmaf(fc.ka, tpost, fc.kb);
+        const float x0v = D * cy * (1.f + sq1ct) * frcp(1.4142135623730951f * fmaf(KC(alpha4), tpost, beta_term));
+        const float kyv = fmaf(KC(ka), tpost, KC(kb));
         const float inv_x0v = frcp(x0v);
-        const float sz0v = fc.near_c * (0.5f / 0.501f);  // 0.5 D sqrt(1/2)
+        const float sz0v = KC(near_c) * (0.5f / 0.501f);  // 0.5 D sqrt(1/2)
         const float sy0v = sz0v * cy;
-        const float near_s = fc.near_c * fsqrt(ct);
-        const float ctc = ct * cy * fc.d2_8;
-        const float watK = fc.ch_const * __powf(a, fc.ch_ai) * I0p;
+        const float near_s = KC(near_c) * fsqrt(ct);
+        const float ctc = ct * cy * KC(d2_8);
+        const float watK = KC(ch_const) * __powf(a, KC(ch_ai)) * I0p;
 
         const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
         const float2 xi = sm.xhl[i], yi = sm.yhl[i];
 
         // ===== sweep of the downstream targets: 10 turbines x 3 lateral columns per pass =====
         for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
-            const int t = t0 + g;
-            const bool active = lane_ok && t < T && t != i;
-            int c = 0;
-            float dx = 0.f, dyc = 0.f;
-            if (active) {
-                const float2 xt = sm.xhl[t], yt = sm.yhl[t];
-                dx = (xt.x - xi.x) + (xt.y - xi.y);
-                dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
-                const float lin = fmaf(fc.bd, dx, fc.ad);
+            const int tr = t0 + g;
+            const bool active = lane_ok && tr < T && tr != i;
+            const int t = min(tr, T - 1);  // inactive lanes compute on a valid turbine; only their stores are masked
+            const float2 xt = sm.xhl[t], yt = sm.yhl[t];
+            const float dx = (xt.x - xi.x) + (xt.y - xi.y);
+            const float dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
+            const float lin = fmaf(KC(bd), dx, KC(ad));
 
-                // -- deflection of source i's wake at this column (both branches, select)
-                float defl;
-                {
-                    const float dd = dx - x0d;
-                    const float sgy = fmaf(kyd, dd, sy0d), sgz = fmaf(kyd, dd, sz0d);
-                    const float sq = fsqrt(sgy * sgz * inv_s0d);
-                    const float L = flg2(A_ln * fmaf(1.6f, sq, -sM0) * frcp(fmaf(1.6f, sq, sM0))) * kLn2;
-                    const float d_far = fmaf(Kck, L, delta0) + lin;
-                    const float d_near = fmaf(dx * inv_x0d, delta0, lin);
-                    defl = (dx <= x0d) ? d_near : d_far;
-                }
-                // -- Gaussian deficit: widths and the lateral factor once per column
-                float base, ek;
-                {
-                    const bool far = dx >= x0v;
-                    const bool near = (t >= near_i) && !far;
-                    const float dd = dx - x0v;
-                    const float up = dx * inv_x0v, down = 1.f - up;
-                    const float sgy = far ? fmaf(kyv, dd, sy0v) : fmaf(down, near_s, up * sy0v);
-                    const float sgz = far ? fmaf(kyv, dd, sz0v) : fmaf(down, near_s, up * sz0v);
-                    const float ry = frcp(sgy), rz = frcp(sgz);
-                    const float dy = dyc - defl;
-                    const float ay = 0.5f * (dy * ry) * (dy * ry);
-                    const float dcl = fclamp(1.f - ctc * ry * rz, 0.f, 1.f);
-                    const float C = 1.f - fsqrt(dcl);
-                    base = (near || far) ? C * fex2(-ay * kLog2e) : 0.f;
-                    ek = fex2(-(0.5f * kLog2e) * fc.dz2[0] * rz * rz);
-                }
-                const float dU0 = base * ek * U0a, dU1 = base * U0b, dU2 = base * ek * U0c;
-                c = (dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f);
+            // -- deflection of source i's wake at this column (both branches, select)
+            float defl;
+            {
+                const float dd = dx - x0d;
+                const float sgy = fmaf(kyd, dd, sy0d), sgz = fmaf(kyd, dd, sz0d);
+                const float sq = fsqrt(sgy * sgz * inv_s0d);
+                const float L = flg2(A_ln * fmaf(1.6f, sq, -sM0) * frcp(fmaf(1.6f, sq, sM0))) * kLn2;
+                const float d_far = fmaf(Kck, L, delta0) + lin;
+                const float d_near = fmaf(dx * inv_x0d, delta0, lin);
+                defl = (dx <= x0d) ? d_near : d_far;
+            }
+            // -- Gaussian deficit: widths and the lateral factor once per column
+            float base, ek;
+            {
+                const bool far = dx >= x0v;
+                const bool near = (t >= near_i) && !far;
+                const float dd = dx - x0v;
+                const float up = dx * inv_x0v, down = 1.f - up;
+                const float sgy = far ? fmaf(kyv, dd, sy0v) : fmaf(down, near_s, up * sy0v);
+                const float sgz = far ? fmaf(kyv, dd, sz0v) : fmaf(down, near_s, up * sz0v);
+                const float ry = frcp(sgy), rz = frcp(sgz);
+                const float dy = (dyc - defl) * ry;
+                const float dcl = fclamp(fmaf(-ctc * ry, rz, 1.f), 0.f, 1.f);
+                const float C = 1.f - fsqrt(dcl);
+                base = (near || far) ? C * fex2((-0.5f * kLog2e) * dy * dy) : 0.f;
+                ek = fex2(c_ek * rz * rz);
+            }
+            const float be = base * ek;
+            const float dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
+            const int c = active ? ((dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f)) : 0;
 
-                // -- transverse velocities of the 6 vortices at the 3 vertical points
-                const float yL = dyc + kNumEpsF;
-                const float q = yL * yL;
-                const float E = fex2(-q * fc.inv_eps2 * kLog2e);
-                float Vk[3], Wk[3];
+            // -- transverse velocities of the 3 vortex pairs (real + ground mirror) at the 3 vertical points
+            const float yL = dyc + kNumEpsF;
+            const float q = yL * yL;
+            const float E = fex2(q * c_e);
+            float Vk[3], Wk[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float r0 = q + fc.zz2[0][k], r1 = q + fc.zz2[1][k], r2 = q + fc.zz2[2][k];
-                    const float r3 = q + fc.zz2[3][k], r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
-                    const float i02 = frcp(r0 * r2), i13 = frcp(r1 * r3), i45 = frcp(r4 * r5);
-                    const float f0 = fmaf(-E, fc.ez[0][k], 1.f) * (r2 * i02);
-                    const float f2 = fmaf(-E, fc.ez[2][k], 1.f) * (r0 * i02);
-                    const float f1 = fmaf(-E, fc.ez[1][k], 1.f) * (r3 * i13);
-                    const float f3 = fmaf(-E, fc.ez[3][k], 1.f) * (r1 * i13);
-                    const float f4 = fmaf(-E, fc.ez[4][k], 1.f) * (r5 * i45);
-                    const float f5 = fmaf(-E, fc.ez[5][k], 1.f) * (r4 * i45);
-                    const float SV = Gt * fmaf(fc.zz[0][k], f0, -fc.zz[2][k] * f2) +
-                                     Gb * fmaf(fc.zz[1][k], f1, -fc.zz[3][k] * f3) +
-                                     Gwr * fmaf(fc.zz[4][k], f4, -fc.zz[5][k] * f5);
-                    const float SW = Gt * (f0 - f2) + Gb * (f1 - f3) + Gwr * (f4 - f5);
-                    const float dec = fc.eps2 * fc.inv_2pi * frcp(fmaf(fc.nu4[k], dx, fc.eps2));
-                    Vk[k] = SV * dec;
-                    Wk[k] = fmaxf(-yL * SW * dec, 0.f);
+            for (int k = 0; k < 3; ++k) {
+                float4 ca, cb, cc, cd;
+                if (BAKED) {  // immediates
+                    ca = make_float4(WfBaked::cblk(16 * k), WfBaked::cblk(16 * k + 1), WfBaked::cblk(16 * k + 2), WfBaked::cblk(16 * k + 3));
+                    cb = make_float4(WfBaked::cblk(16 * k + 4), WfBaked::cblk(16 * k + 5), WfBaked::cblk(16 * k + 6), WfBaked::cblk(16 * k + 7));
+                    cc = make_float4(WfBaked::cblk(16 * k + 8), WfBaked::cblk(16 * k + 9), WfBaked::cblk(16 * k + 10), WfBaked::cblk(16 * k + 11));
+                    cd = make_float4(WfBaked::cblk(16 * k + 12), WfBaked::cblk(16 * k + 13), WfBaked::cblk(16 * k + 14), WfBaked::cblk(16 * k + 15));
+                } else {      // LDS.128 broadcast from the shared-memory block
+                    ca = sm.cblk[4 * k]; cb = sm.cblk[4 * k + 1]; cc = sm.cblk[4 * k + 2]; cd = sm.cblk[4 * k + 3];
                 }
-                // -- state update of this column's 3 points
+                const float r0 = q + ca.x, r2 = q + ca.y, r1 = q + ca.z, r3 = q + ca.w, r4 = q + cb.x, r5 = q + cb.y;
+                const float g0 = Gt * frcp(r0 * r2), g1 = Gb * frcp(r1 * r3), g4 = Gwr * frcp(r4 * r5);
+                const float X0 = fmaf(-E, cb.z, 1.f) * r2, X1 = fmaf(-E, cb.w, 1.f) * r3, X4 = fmaf(-E, cc.x, 1.f) * r5;
+                const float NV0 = fmaf(cc.y, X0, -(cc.z * r0)), NV1 = fmaf(cc.w, X1, -(cd.x * r1));
+                const float NV4 = fmaf(cd.y, X4, -(cd.z * r4));
+                const float SV = fmaf(g4, NV4, fmaf(g1, NV1, g0 * NV0));
+                const float SW = fmaf(g4, X4 - r4, fmaf(g1, X1 - r1, g0 * (X0 - r0)));
+                const float dec = c_dec * frcp(fmaf(cd.w, dx, eps2));
+                Vk[k] = SV * dec;
+                Wk[k] = fmaxf(SW * (-yL * dec), 0.f);
+            }
+            // -- state update of this column's 3 points
+            if (active) {
                 const int qb = 9 * t + 3 * j;
                 sm.wsq[qb] = fmaf(dU0, dU0, sm.wsq[qb]);
                 sm.wsq[qb + 1] = fmaf(dU1, dU1, sm.wsq[qb + 1]);
@@ -334,8 +361,8 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
             const int gb = 3 * g;
             const int c_tot = __shfl_sync(0xffffffffu, c, gb & 31) + __shfl_sync(0xffffffffu, c, (gb + 1) & 31) +
                               __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
-            if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabsf(dyc) < fc.two_D) {
-                const float wat = watK * __powf(dx * fc.inv_D, fc.ch_down);
+            if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabsf(dyc) < KC(two_D)) {
+                const float wat = watK * __powf(dx * KC(inv_D), KC(ch_down));
                 const float ta = (float)c_tot * (1.f / 9.f) * wat;
                 sm.tia[3 * t + j] = fmaxf(sm.tia[3 * t + j], ta);
             }
@@ -433,33 +460,47 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
 
 }  // namespace
 
-cudaError_t wf_launch_step_fast(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
-                                const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                const WfOutPtrs& out, cudaStream_t stream) {
+template <bool BAKED>
+static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
+                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                 const WfOutPtrs& out, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes(m.T);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    wf_step_fast_kernel<<<m.B, 32, smem, stream>>>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    wf_step_fast_kernel<BAKED><<<m.B, 32, smem, stream>>>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
-cudaError_t wf_step_fast_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
-                                    int* smem) {
+cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
+                                const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                const WfOutPtrs& out, cudaStream_t stream) {
+    return baked ? launch_fast_t<true>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, stream)
+                 : launch_fast_t<false>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, stream);
+}
+
+template <bool BAKED>
+static cudaError_t attrs_fast_t(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads, int* smem) {
     *threads = 32;
     *smem = (int)fast_smem_bytes(m.T);
-    cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(attr, wf_step_fast_kernel);
+    e = cudaFuncGetAttributes(attr, wf_step_fast_kernel<BAKED>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast_kernel, 32, *smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast_kernel<BAKED>, 32, *smem);
+}
+
+cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm,
+                                    int* threads, int* smem) {
+    return baked ? attrs_fast_t<true>(m, attr, ctas_per_sm, threads, smem)
+                 : attrs_fast_t<false>(m, attr, ctas_per_sm, threads, smem);
 }
