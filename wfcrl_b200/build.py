@@ -47,7 +47,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         fp.write(subprocess.run([gen_exe], check=True, capture_output=True, text=True).stdout)
     os.remove(gen_exe)
     # step 2: the library
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("WFCRL_NVCC_EXTRA", "").split()  # e.g. -DWF_FAST_MINB=14 for tuning experiments
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fp:

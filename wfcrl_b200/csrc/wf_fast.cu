@@ -32,6 +32,9 @@ constexpr float kDeg = 57.29577951308232f;
 constexpr float kRad = 0.017453292519943295f;
 constexpr float kNumEpsF = 0.001f;
 constexpr int kTurbPerPass = 10;
+#ifndef WF_FAST_MINB
+#define WF_FAST_MINB 16  // resident env-CTAs per SM the register allocation is tuned for
+#endif
 
 __device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fsqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -64,6 +67,7 @@ struct SmemView {
     float *ynew;              // [T] new yaw, degrees, ORIGINAL order
     uchar4* idx;              // [T]
     unsigned char* ordr;      // [T]
+    unsigned char* queue;     // [T] targets whose rotor can see source i's velocity deficit (compacted per source)
     float4* cblk;             // [12] per-model vortex constants, 4 float4 per vertical index k (LDS.128 broadcast)
 };
 
@@ -74,7 +78,8 @@ __host__ __device__ inline size_t fast_smem_bytes(int T) {
     n += (size_t)3 * T * 4;      // tia
     n += (size_t)5 * T * 4;      // cyaw, syaw, yawr, tifin, ynew
     n += (size_t)T * 4;          // idx
-    n += (size_t)((T + 15) / 16 * 16);
+    n += (size_t)((T + 15) / 16 * 16);  // ordr
+    n += (size_t)((T + 15) / 16 * 16);  // queue
     return (n + 15) / 16 * 16;
 }
 
@@ -96,11 +101,12 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
     s.ynew = f; f += T;
     s.idx = (uchar4*)f; f += T;
     s.ordr = (unsigned char*)f;
+    s.queue = s.ordr + (T + 15) / 16 * 16;
     return s;
 }
 
 template <bool BAKED>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, WF_FAST_MINB)
 wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfFastConst fc, const WfState s,
                     const uint8_t* __restrict__ mask, const float* __restrict__ action,
                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
@@ -280,7 +286,16 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
         const float2 xi = sm.xhl[i], yi = sm.yhl[i];
 
-        // ===== sweep of the downstream targets: 10 turbines x 3 lateral columns per pass =====
+        // Conservative lateral reach of this source's velocity deficit at column j: the Gaussian factor is below
+        // exp(-kCut^2/2) (2.7e-7) when |Y - y_i| > kCut * sigma_y_bound(dx) + |deflection|_max.  sigma_y <= kyv*dx +
+        // max(sigma_y0, near-wake width); |deflection| <= |delta0| + |Kc/ky| * ln(A_ln) (+ |ad + bd dx|).
+        constexpr float kCut = 5.5f;
+        const float reach1 = kCut * kyv;
+        const float reach0 = fmaf(kCut, fmaxf(near_s, sy0v), fabsf(delta0) + fabsf(Kck) * (flg2(A_ln) * kLn2));
+
+        // ===== V sweep: transverse velocities on ALL downstream targets, 10 turbines x 3 lateral columns per pass;
+        //       builds the compacted queue of targets that can see the velocity deficit =====
+        int qn = 0;
         for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
             const int tr = t0 + g;
             const bool active = lane_ok && tr < T && tr != i;
@@ -288,40 +303,16 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
             const float2 xt = sm.xhl[t], yt = sm.yhl[t];
             const float dx = (xt.x - xi.x) + (xt.y - xi.y);
             const float dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
-            const float lin = fmaf(KC(bd), dx, KC(ad));
 
-            // -- deflection of source i's wake at this column (both branches, select)
-            float defl;
-            {
-                const float dd = dx - x0d;
-                const float sgy = fmaf(kyd, dd, sy0d), sgz = fmaf(kyd, dd, sz0d);
-                const float sq = fsqrt(sgy * sgz * inv_s0d);
-                const float L = flg2(A_ln * fmaf(1.6f, sq, -sM0) * frcp(fmaf(1.6f, sq, sM0))) * kLn2;
-                const float d_far = fmaf(Kck, L, delta0) + lin;
-                const float d_near = fmaf(dx * inv_x0d, delta0, lin);
-                defl = (dx <= x0d) ? d_near : d_far;
-            }
-            // -- Gaussian deficit: widths and the lateral factor once per column
-            float base, ek;
-            {
-                const bool far = dx >= x0v;
-                const bool near = (t >= near_i) && !far;
-                const float dd = dx - x0v;
-                const float up = dx * inv_x0v, down = 1.f - up;
-                const float sgy = far ? fmaf(kyv, dd, sy0v) : fmaf(down, near_s, up * sy0v);
-                const float sgz = far ? fmaf(kyv, dd, sz0v) : fmaf(down, near_s, up * sz0v);
-                const float ry = frcp(sgy), rz = frcp(sgz);
-                const float dy = (dyc - defl) * ry;
-                const float dcl = fclamp(fmaf(-ctc * ry, rz, 1.f), 0.f, 1.f);
-                const float C = 1.f - fsqrt(dcl);
-                base = (near || far) ? C * fex2((-0.5f * kLog2e) * dy * dy) : 0.f;
-                ek = fex2(c_ek * rz * rz);
-            }
-            const float be = base * ek;
-            const float dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
-            const int c = active ? ((dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f)) : 0;
+            const bool need = active && (t >= near_i) &&
+                              (fabsf(dyc) < fmaf(reach1, dx, reach0) + fabsf(fmaf(KC(bd), dx, KC(ad))));
+            const unsigned nb = __ballot_sync(0xffffffffu, need);
+            const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
+            const unsigned lb = __ballot_sync(0xffffffffu, leader);
+            if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
+            qn += __popc(lb);
 
-            // -- transverse velocities of the 3 vortex pairs (real + ground mirror) at the 3 vertical points
+            // transverse velocities of the 3 vortex pairs (real + ground mirror) at the 3 vertical points
             const float yL = dyc + kNumEpsF;
             const float q = yL * yL;
             const float E = fex2(q * c_e);
@@ -348,14 +339,59 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
                 Vk[k] = SV * dec;
                 Wk[k] = fmaxf(SW * (-yL * dec), 0.f);
             }
-            // -- state update of this column's 3 points
             if (active) {
+                const int qb = 9 * t + 3 * j;
+                sm.v[qb] += Vk[0]; sm.v[qb + 1] += Vk[1]; sm.v[qb + 2] += Vk[2];
+                sm.w[qb] += Wk[0]; sm.w[qb + 1] += Wk[1]; sm.w[qb + 2] += Wk[2];
+            }
+        }
+        __syncwarp();
+
+        // ===== D sweep: deflection + Gaussian deficit + wake-added TI, only on the queued targets =====
+        for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
+            const int e = q0 + g;
+            const bool active = lane_ok && e < qn;
+            const int t = sm.queue[min(e, qn - 1)];
+            const float2 xt = sm.xhl[t], yt = sm.yhl[t];
+            const float dx = (xt.x - xi.x) + (xt.y - xi.y);
+            const float dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
+            const float lin = fmaf(KC(bd), dx, KC(ad));
+
+            // -- deflection of source i's wake at this column (both branches, select)
+            float defl;
+            {
+                const float dd = dx - x0d;
+                const float sgy = fmaf(kyd, dd, sy0d), sgz = fmaf(kyd, dd, sz0d);
+                const float sq = fsqrt(sgy * sgz * inv_s0d);
+                const float L = flg2(A_ln * fmaf(1.6f, sq, -sM0) * frcp(fmaf(1.6f, sq, sM0))) * kLn2;
+                const float d_far = fmaf(Kck, L, delta0) + lin;
+                const float d_near = fmaf(dx * inv_x0d, delta0, lin);
+                defl = (dx <= x0d) ? d_near : d_far;
+            }
+            // -- Gaussian deficit: widths and the lateral factor once per column (queued targets have t >= near_i)
+            float base, ek;
+            {
+                const bool far = dx >= x0v;
+                const float dd = dx - x0v;
+                const float up = dx * inv_x0v, down = 1.f - up;
+                const float sgy = far ? fmaf(kyv, dd, sy0v) : fmaf(down, near_s, up * sy0v);
+                const float sgz = far ? fmaf(kyv, dd, sz0v) : fmaf(down, near_s, up * sz0v);
+                const float ry = frcp(sgy), rz = frcp(sgz);
+                const float dy = (dyc - defl) * ry;
+                const float dcl = fclamp(fmaf(-ctc * ry, rz, 1.f), 0.f, 1.f);
+                const float C = 1.f - fsqrt(dcl);
+                base = C * fex2((-0.5f * kLog2e) * dy * dy);
+                ek = fex2(c_ek * rz * rz);
+            }
+            const float be = base * ek;
+            const float dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
+            int c = 0;
+            if (active) {
+                c = (dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f);
                 const int qb = 9 * t + 3 * j;
                 sm.wsq[qb] = fmaf(dU0, dU0, sm.wsq[qb]);
                 sm.wsq[qb + 1] = fmaf(dU1, dU1, sm.wsq[qb + 1]);
                 sm.wsq[qb + 2] = fmaf(dU2, dU2, sm.wsq[qb + 2]);
-                sm.v[qb] += Vk[0]; sm.v[qb + 1] += Vk[1]; sm.v[qb + 2] += Vk[2];
-                sm.w[qb] += Wk[0]; sm.w[qb + 1] += Wk[1]; sm.w[qb + 2] += Wk[2];
             }
             // -- Crespo-Hernandez wake-added TI: overlap = (#points with deficit*U0 > 0.05) / 9 over the 3 columns
             const int gb = 3 * g;
