@@ -45,6 +45,19 @@ def algorithmic_bytes(T: int) -> int:
     return 48 * T + 16
 
 
+def _ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu --set full capture
+    of this same command (profiles/ncu_traffic.json, written by hand from `ncu -i ... --page raw`); None if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fp:
+            rec = json.load(fp)[kernel]
+        return {"bytes_per_launch": rec["dram_bytes_read"] + rec["dram_bytes_write"], "source": rec["source"],
+                "algorithmic_bytes_per_launch": rec.get("algorithmic_bytes")}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # nvidia-smi clock sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ------------------------------------------------------------------------------------------------------------------
@@ -366,7 +379,7 @@ def run_ours(args):
                      "unit": "G special/s"},
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "frac": hbm_ach / hbm_peak, "unit": "GB/s",
                     "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
-            "traffic": None,
+            "traffic": _ncu_traffic(args.kernel),
             "avg_launch_ms": total_ms / max(launches, 1),
             "occupancy": info,
         }

@@ -44,7 +44,7 @@ struct WfHandle_t {
     float* d_action = nullptr;
     double* d_yaw_cmd = nullptr;
     WfOutPtrs d_out = {};
-    cudaStream_t host_stream = nullptr;
+    cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
     uint64_t launches = 0;
 };
 
@@ -85,6 +85,7 @@ int wf_destroy(WfHandle h) {
     if (h->h_rwd) cudaFreeHost(h->h_rwd);
     if (h->h_rcs) cudaFreeHost(h->h_rcs);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
     delete h;
     return WF_OK;
 }
@@ -178,7 +179,8 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         cudaMallocHost((void**)&h->h_rwd, sizeof(double) * B) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_rcs, sizeof(double) * 2 * B) != cudaSuccess)
         return fail(set_err(WF_ERR_NOMEM, "cudaMallocHost failed"));
-    if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking) != cudaSuccess)
         return fail(set_err(WF_ERR_CUDA, "cudaStreamCreate failed"));
 
     // initial condition: wind (8, 270) as in FlorisCase.simul_params (data_cases.py:99-100), ambient TI from the config
@@ -209,12 +211,15 @@ static WfOutPtrs to_ptrs(const WfStepOut* o) {
 }
 
 static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float* d_action, const double* d_yaw,
-                       const WfOutPtrs& out, cudaStream_t st) {
+                       const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1) {
+    if (env_count < 0) env_count = h->model.B;
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST)
-        e = wf_launch_step_fast(mode, h->fast_baked, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, st);
+        e = wf_launch_step_fast(mode, h->fast_baked, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
+                                env_count, st);
     else
-        e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, st);
+        e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, env_begin,
+                                 env_count, st);
     h->launches += 1;
     if (e != cudaSuccess) return set_err(WF_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
     return WF_OK;
@@ -293,16 +298,8 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
         TRY(dev_alloc(h, &p, 2 * B * es)); h->d_out.freewind = p;
         TRY(dev_alloc(h, &h->d_out.truncated, B));
     }
-    cudaStream_t st = h->host_stream;
+    // Chunked two-stream pipeline: the device->host copies of chunk c overlap the kernel of chunk c+1.
     uint64_t up = 0, down = 0;
-    if (h_action) {
-        CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, sizeof(float) * BT, cudaMemcpyHostToDevice, st));
-        up += sizeof(float) * BT;
-    }
-    if (h_yaw) {
-        CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd, h_yaw, sizeof(double) * BT, cudaMemcpyHostToDevice, st));
-        up += sizeof(double) * BT;
-    }
     WfOutPtrs o = {};
     if (ho->yaw) o.yaw = h->d_out.yaw;
     if (ho->wind_speed) o.wind_speed = h->d_out.wind_speed;
@@ -312,16 +309,33 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
     if (ho->reward) o.reward = h->d_out.reward;
     if (ho->freewind) o.freewind = h->d_out.freewind;
     if (ho->truncated) o.truncated = h->d_out.truncated;
-    TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st));
-#define D2H(field, bytes)                                                                              \
-    if (ho->field) {                                                                                   \
-        CUDA_TRY(cudaMemcpyAsync(ho->field, h->d_out.field, (bytes), cudaMemcpyDeviceToHost, st));      \
-        down += (bytes);                                                                               \
+    const int nchunk = (B >= 2048) ? 4 : 1;
+    cudaStream_t streams[2] = {h->host_stream, h->host_stream2};
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
+        cudaStream_t st = streams[c & 1];
+        if (h_action) {
+            CUDA_TRY(cudaMemcpyAsync(h->d_action + b0 * T, h_action + b0 * T, sizeof(float) * nb * T, cudaMemcpyHostToDevice, st));
+            up += sizeof(float) * nb * T;
+        }
+        if (h_yaw) {
+            CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd + b0 * T, h_yaw + b0 * T, sizeof(double) * nb * T, cudaMemcpyHostToDevice, st));
+            up += sizeof(double) * nb * T;
+        }
+        TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st,
+                        (int)b0, (int)nb));
+#define D2H(field, per_env)                                                                                       \
+    if (ho->field) {                                                                                              \
+        const size_t off = b0 * (per_env), bytes = nb * (per_env);                                                \
+        CUDA_TRY(cudaMemcpyAsync((char*)ho->field + off, (char*)h->d_out.field + off, bytes, cudaMemcpyDeviceToHost, st)); \
+        down += bytes;                                                                                            \
     }
-    D2H(yaw, BT * es) D2H(wind_speed, BT * es) D2H(wind_direction, BT * es) D2H(power, BT * es) D2H(load, 4 * BT * es)
-    D2H(reward, B * es) D2H(freewind, 2 * B * es) D2H(truncated, B)
+        D2H(yaw, T * es) D2H(wind_speed, T * es) D2H(wind_direction, T * es) D2H(power, T * es) D2H(load, 4 * T * es)
+        D2H(reward, es) D2H(freewind, 2 * es) D2H(truncated, 1)
 #undef D2H
-    CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(streams[0]));
+    if (nchunk > 1) CUDA_TRY(cudaStreamSynchronize(streams[1]));
     if (h2d) *h2d = up;
     if (d2h) *d2h = down;
     return WF_OK;

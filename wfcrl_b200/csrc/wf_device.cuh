@@ -97,7 +97,7 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
                                cudaStream_t stream);
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
-                                 cudaStream_t stream);
+                                 int env_begin, int env_count, cudaStream_t stream);
 cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                const double* d_wd, cudaStream_t stream);
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
@@ -105,6 +105,6 @@ cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);
 cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                const WfOutPtrs& out, cudaStream_t stream);
+                                const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
 cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);

@@ -59,7 +59,8 @@ __device__ __forceinline__ float interp_f(const WfFastConst& fc, const float* __
 }
 
 struct SmemView {
-    float *wsq, *v, *w;       // [9T] per rotor point, q = 9 t + 3 j + k
+    float* wsq;               // [9T] per rotor point, q = 9 t + 3 j + k: running sum of squared deficits
+    float2* vw;               // [9T] (v, w) per rotor point (8-byte pairs: one LDS.64 / STS.64 per point)
     float2 *xhl, *yhl;        // [T]
     float *tia;               // [3T] running max of the wake-added TI per (turbine, lateral column)
     float *cyaw, *syaw, *yawr;  // [T] cos / sin / radians of the yaw (sorted order)
@@ -89,10 +90,9 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
     float2* f2 = (float2*)(base + 12 * 16);
     s.xhl = f2;
     s.yhl = f2 + T;
-    float* f = (float*)(f2 + 2 * T);
+    s.vw = f2 + 2 * T;  // 8-byte aligned for every T
+    float* f = (float*)(f2 + 2 * T + 9 * T);
     s.wsq = f; f += 9 * T;
-    s.v = f; f += 9 * T;
-    s.w = f; f += 9 * T;
     s.tia = f; f += 3 * T;
     s.cyaw = f; f += T;
     s.syaw = f; f += T;
@@ -107,10 +107,10 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
 
 template <bool BAKED>
 __global__ void __launch_bounds__(32, WF_FAST_MINB)
-wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfFastConst fc, const WfState s,
-                    const uint8_t* __restrict__ mask, const float* __restrict__ action,
+wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const __grid_constant__ WfFastConst fc,
+                    const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
-    const int b = blockIdx.x;
+    const int b = blockIdx.x + env_begin;
     if (mask && !mask[b]) return;
     const int T = m.T;
     const int lane = threadIdx.x;
@@ -150,7 +150,7 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         sm.ordr[tt] = (unsigned char)s.order[row + tt];
     }
     if (lane < 12) sm.cblk[lane] = make_float4(fc.cblk[4 * lane], fc.cblk[4 * lane + 1], fc.cblk[4 * lane + 2], fc.cblk[4 * lane + 3]);
-    for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.f; sm.v[q] = 0.f; sm.w[q] = 0.f; }
+    for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.f; sm.vw[q] = make_float2(0.f, 0.f); }
     for (int q = lane; q < 3 * T; q += 32) sm.tia[q] = 0.f;
     __syncwarp();
     for (int tt = lane; tt < T; tt += 32) {
@@ -194,8 +194,9 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         float su3, sv, sw, vq, wwq;
         {
             const float wq = sm.wsq[9 * i + plc];
-            vq = sm.v[9 * i + plc];
-            wwq = sm.w[9 * i + plc];
+            const float2 vw0 = sm.vw[9 * i + plc];
+            vq = vw0.x;
+            wwq = vw0.y;
             const float u = U0p - fsqrt(wq);
             su3 = pv ? u * u * u : 0.f;
             sv = pv ? vq : 0.f;
@@ -262,7 +263,7 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
 #pragma unroll
             for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
             sumW += rw;
-            if (lane < 9) { sm.v[9 * i + lane] = vq + Vs; sm.w[9 * i + lane] = wwq + Ws; }
+            if (lane < 9) sm.vw[9 * i + lane] = make_float2(vq + Vs, wwq + Ws);
         }
         const float aI = avg * tp0;
         const float kk2 = 3.f * aI * aI;  // u_term^2 = 2 k = 2 (avg I)^2 / (2/3)
@@ -341,8 +342,11 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
             }
             if (active) {
                 const int qb = 9 * t + 3 * j;
-                sm.v[qb] += Vk[0]; sm.v[qb + 1] += Vk[1]; sm.v[qb + 2] += Vk[2];
-                sm.w[qb] += Wk[0]; sm.w[qb + 1] += Wk[1]; sm.w[qb + 2] += Wk[2];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float2 o = sm.vw[qb + k];
+                    sm.vw[qb + k] = make_float2(o.x + Vk[k], o.y + Wk[k]);
+                }
             }
         }
         __syncwarp();
@@ -417,8 +421,9 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
         for (int p = 0; p < 9; ++p) {
             const float U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
             u[p] = U0k - fsqrt(sm.wsq[9 * tt + p]);
-            vv[p] = sm.v[9 * tt + p];
-            ww[p] = sm.w[9 * tt + p];
+            const float2 vwp = sm.vw[9 * tt + p];
+            vv[p] = vwp.x;
+            ww[p] = vwp.y;
             su += u[p];
             su3 = fmaf(u[p] * u[p], u[p], su3);
             svv += vv[p];
@@ -499,7 +504,7 @@ wf_step_fast_kernel(const int mode, const WfModel m, const __grid_constant__ WfF
 template <bool BAKED>
 static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                  const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                 const WfOutPtrs& out, cudaStream_t stream) {
+                                 const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes(m.T);
     static bool configured[64] = {};
     int dev = 0;
@@ -512,15 +517,15 @@ static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& 
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    wf_step_fast_kernel<BAKED><<<m.B, 32, smem, stream>>>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    wf_step_fast_kernel<BAKED><<<env_count, 32, smem, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
 cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                const WfOutPtrs& out, cudaStream_t stream) {
-    return baked ? launch_fast_t<true>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, stream)
-                 : launch_fast_t<false>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, stream);
+                                const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
+    return baked ? launch_fast_t<true>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream)
+                 : launch_fast_t<false>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream);
 }
 
 template <bool BAKED>

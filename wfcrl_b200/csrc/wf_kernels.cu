@@ -266,9 +266,10 @@ __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const ui
 // ---------------------------------------------------------------------------------------------------------------
 template <typename R>
 __global__ void __launch_bounds__(WF_MAX_TURBINES_K)
-wf_step_basic_kernel(const int mode, const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
-                     const float* __restrict__ action, const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
-    const int b = blockIdx.x;
+wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const WfState s,
+                     const uint8_t* __restrict__ mask, const float* __restrict__ action,
+                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
+    const int b = blockIdx.x + env_begin;
     if (mask && !mask[b]) return;
     const int T = m.T;
     const int t = threadIdx.x;
@@ -702,12 +703,12 @@ cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint
 
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
-                                 cudaStream_t stream) {
+                                 int env_begin, int env_count, cudaStream_t stream) {
     const int threads = round_up_warp(m.T);
     if (precision == 0)
-        wf_step_basic_kernel<double><<<m.B, threads, 0, stream>>>(mode, m, s, d_mask, d_action, d_yaw_cmd, out);
+        wf_step_basic_kernel<double><<<env_count, threads, 0, stream>>>(mode, env_begin, m, s, d_mask, d_action, d_yaw_cmd, out);
     else
-        wf_step_basic_kernel<float><<<m.B, threads, 0, stream>>>(mode, m, s, d_mask, d_action, d_yaw_cmd, out);
+        wf_step_basic_kernel<float><<<env_count, threads, 0, stream>>>(mode, env_begin, m, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
