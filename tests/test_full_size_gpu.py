@@ -1,0 +1,109 @@
+"""GPU tests at BASELINE.json's full batch sizes: direct oracle comparison on a random subset of envs plus
+size-independent properties (determinism, env-permutation invariance, yaw-bound saturation, energy sanity)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from tests._util import host_trig, layout, sample_winds
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # BASELINE.json configs[1..4]: (layout, envs, precision, kernel)
+    ("Ablaincourt_", 4096, "f32", "fast"),
+    ("Turb16_TCRWP_", 16384, "f32", "fast"),
+    ("Turb32_Row5_", 8192, "f64", "basic"),
+    ("HornsRev1_", 8192, "f32", "fast"),
+]
+
+
+@pytest.mark.parametrize("name,B,precision,kernel", CASES)
+def test_full_batch_against_oracle_subset_and_properties(cuda_device, name, B, precision, kernel):
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout(name)
+    T = len(lx)
+    ws, wd = sample_winds(B, seed=21, tie_every=97)
+    rng = np.random.default_rng(22)
+    yaw0 = rng.uniform(-40, 40, (B, T)).astype(np.float32)
+    act = rng.uniform(-5, 5, (B, T)).astype(np.float32)
+    fb = FlorisBatch(lx, ly, B, precision=precision, kernel=kernel, max_iter=100)
+    fb.reset(ws, wd, host_trig=True)
+    fb.set_state("yaw", yaw0.astype(np.float64))
+    out = fb.step(torch.as_tensor(act, device="cuda"))
+    torch.cuda.synchronize()
+    got = {k: v.double().cpu().numpy() for k, v in out.items()}
+
+    # (1) oracle on a random subset (C restatement, same rotation, yaw after the float32 transition)
+    sub = rng.choice(B, size=256, replace=False)
+    yaw1 = np.clip(np.clip(yaw0, -40, 40) + np.clip(act, -5, 5), -40, 40).astype(np.float32)
+    assert np.array_equal(got["yaw"].astype(np.float32), yaw1)  # bit-exact float32 transition for the WHOLE batch
+    c, s = host_trig(wd[sub])
+    ref = c_oracle.solve_batch(lx, ly, ws[sub], wd[sub], yaw1[sub].astype(np.float64), cs=np.stack([c, s], 1))
+    perr = np.abs(got["power"][sub] * 1e6 - ref["power_W"]) / np.maximum(ref["power_W"], 1.0)
+    tol = 1e-9 if precision == "f64" else 1e-4
+    # FP32: allow a vanishing fraction of threshold flips of the wake-overlap count
+    frac_bad = np.mean(perr > tol)
+    assert frac_bad <= (0.0 if precision == "f64" else 2e-3), (frac_bad, perr.max())
+    assert np.median(perr) < (1e-12 if precision == "f64" else 2e-6)
+    loads = np.stack([ref["ti"], ref["std_u"], ref["std_v"], ref["std_w"]], -1)
+    reward = np.mean(ref["power_W"] / 1e6 * 1e3 / np.clip(ws[sub], 3, 28)[:, None] ** 3, 1) - 0.1 * np.mean(np.abs(loads), (1, 2))
+    rerr = np.abs(got["reward"][sub] - reward) / np.abs(reward)
+    assert np.mean(rerr > tol) <= (0.0 if precision == "f64" else 2e-3) and np.median(rerr) < (1e-12 if precision == "f64" else 2e-6)
+    assert np.array_equal(fb.get_state("order")[sub], ref["order"])
+
+    # (2) determinism: same state + action -> bitwise identical outputs
+    fb.reset(ws, wd, host_trig=True)
+    fb.set_state("yaw", yaw0.astype(np.float64))
+    out2 = fb.step(torch.as_tensor(act, device="cuda"))
+    torch.cuda.synchronize()
+    for k in ("power", "reward", "wind_speed", "wind_direction", "load"):
+        assert np.array_equal(out2[k].double().cpu().numpy(), got[k]), k
+
+    # (3) env-permutation invariance: envs are independent, so permuting the batch permutes the results
+    perm = rng.permutation(B)
+    fb.reset(ws[perm], wd[perm], host_trig=True)
+    fb.set_state("yaw", yaw0[perm].astype(np.float64))
+    out3 = fb.step(torch.as_tensor(act[perm], device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(out3["power"].double().cpu().numpy(), got["power"][perm])
+    assert np.array_equal(out3["reward"].double().cpu().numpy(), got["reward"][perm])
+
+    # (4) physical sanity on the whole batch
+    assert np.all(np.isfinite(got["power"])) and np.all(got["power"] >= 0) and np.all(got["power"] <= 5.01)
+    assert np.all(got["wind_speed"] <= ws[:, None] * 1.07 + 1e-6) and np.all(got["wind_speed"] > 0)
+    assert np.all(got["load"][..., 0] >= 0.06 - 1e-6)
+    assert not got["truncated"].any()
+    fb.close()
+
+
+def test_saturation_and_long_episode_counters(cuda_device):
+    """Always push +5 deg: the actuation constraint and the +-40 clip must hold for every env for a whole 500-step episode
+    and truncation must fire exactly at step 499 (reset consumed one iteration)."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb6_Row2_")
+    B, T = 512, len(lx)
+    ws, wd = sample_winds(B, seed=3)
+    fb = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=500)
+    fb.reset(ws, wd, host_trig=False)
+    act = torch.full((B, T), 5.0, device="cuda")
+    first_trunc = None
+    for k in range(499):
+        out = fb.step(act)
+        if k % 50 == 49 or k >= 497:
+            torch.cuda.synchronize()
+            yaw = out["yaw"].cpu().numpy()
+            assert yaw.max() <= 40.0 and yaw.min() >= 0.0
+            if out["truncated"].any() and first_trunc is None:
+                first_trunc = k
+                assert bool(out["truncated"].all())
+    assert first_trunc == 498
+    acc = fb.get_state("acc")
+    # the constraint caps the duty: acc <= 1.8 * moves + one step
+    assert acc.max() <= 1.8 * 499 + 5.0 + 1e-3
+    assert np.all(fb.get_state("num_iter") == 500) and np.all(fb.get_state("num_moves") == 499)
+    fb.close()
