@@ -1,0 +1,25 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel, both precisions."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from wfcrl_b200.backend import FlorisBatch
+from wfcrl_b200.layouts import layout_xy
+
+for name, prec, kern in (("Turb6_Row2_", "f64", "basic"), ("Ablaincourt_", "f32", "fast"), ("HornsRev1_", "f32", "fast"),
+                         ("HornsRev2_", "f32", "fast")):
+    lx, ly = layout_xy(name)
+    B, T = 6, len(lx)
+    fb = FlorisBatch(lx, ly, B, precision=prec, kernel=kern, max_iter=5)
+    rng = np.random.default_rng(0)
+    fb.reset(np.clip(8 * rng.weibull(8, B), 3, 28), rng.normal(270, 20, B) % 360)
+    for k in range(5):
+        out = fb.step(torch.as_tensor(rng.uniform(-5, 5, (B, T)).astype(np.float32), device="cuda"))
+    mask = out["truncated"].clone()
+    fb.reset_masked(mask, torch.full((B,), 9.0, dtype=torch.float64, device="cuda"),
+                    torch.full((B,), 265.0, dtype=torch.float64, device="cuda"))
+    fb.step_host(torch.zeros(B, T).pin_memory())
+    torch.cuda.synchronize()
+    print(name, prec, kern, "ok", float(out["reward"].sum()))
+    fb.close()
