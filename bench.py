@@ -370,7 +370,7 @@ def run_ours(args):
         mufu_ach = per_gpu * w_sp
         hbm_ach = per_gpu * algorithmic_bytes(T) / 1e9
         roofline = {
-            "bound": "fp32_issue", "kernel": "wf_step_fast_kernel" if args.kernel == "fast" else "wf_step_basic_kernel",
+            "bound": "fp32_issue", "kernel": ("wf_step_fast64_kernel" if precision == "f64" else "wf_step_fast_kernel") if args.kernel == "fast" else "wf_step_basic_kernel",
             "achieved": fp32_ach / 1e9, "peak": fp32_peak / 1e9, "unit": "G lane-op/s", "frac": fp32_ach / fp32_peak,
             "frac_at_observed_clock": fp32_ach / (info["sm_count"] * 128 * sm_mhz * 1e6),
             "peak_basis": f"{info['sm_count']} SMs x 128 FP32 lanes x {sm_max_mhz:.0f} MHz (clocks.max.sm); canonical work "
@@ -432,8 +432,6 @@ def main():
     ap.add_argument("--kernel", default="fast", choices=["fast", "basic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.precision == "f64":
-        args.kernel = "basic"
     if args.impl == "reference":
         run_reference(args)
     else:

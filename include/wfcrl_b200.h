@@ -37,7 +37,8 @@ enum WfStatus { WF_OK = 0, WF_ERR_INVALID = 1, WF_ERR_CUDA = 2, WF_ERR_NOMEM = 3
 enum WfPrecision { WF_PREC_F64 = 0, WF_PREC_F32 = 1 };
 /* reward shapers of wfcrl/rewards.py:16-46 */
 enum WfShaper { WF_SHAPER_NONE = 0, WF_SHAPER_REFERENCE_PCT = 1, WF_SHAPER_STEP_PCT = 2 };
-/* kernel variants: 0 = straightforward one-thread-per-turbine kernel (FP64 and FP32), 1 = tuned FP32 kernel */
+/* kernel variants: 0 = straightforward one-thread-per-turbine kernel (FP64 and FP32), 1 = tuned warp-per-env kernel
+ * (FP32 fast mode, or its FP64 instantiation for the bit-check mode) */
 enum WfKernel { WF_KERNEL_BASIC = 0, WF_KERNEL_FAST = 1 };
 
 /*
@@ -51,7 +52,7 @@ typedef struct WfConfig {
     int32_t num_envs;           /* B: environments resident on this device (the local shard) */
     int32_t device;             /* CUDA device ordinal */
     int32_t precision;          /* enum WfPrecision */
-    int32_t kernel;             /* enum WfKernel (WF_KERNEL_FAST requires WF_PREC_F32) */
+    int32_t kernel;             /* enum WfKernel */
     int32_t max_iter;           /* interface.max_iter = start_iter + max_num_steps (simple_env.py:33, interface.py:586) */
     int32_t continuous_control; /* mdp.py:300-310: 1 = Box actions clipped to +-step, 0 = {0,1,2} -> (a-1)*step */
     int32_t multi_agent;        /* 1 = actuation constraint with the per-agent staleness of multiagent_env.py:198-249 */

@@ -20,7 +20,8 @@ def _oracle_envs(name, B, ws, wd, **kw):
 
 
 @pytest.mark.parametrize("name,precision,kernel,steps", [
-    ("Turb6_Row2_", "f64", "basic", 30), ("Turb6_Row2_", "f32", "fast", 30),
+    ("Turb6_Row2_", "f64", "basic", 30), ("Turb6_Row2_", "f64", "fast", 30), ("Turb6_Row2_", "f32", "fast", 30),
+    ("Ablaincourt_", "f64", "fast", 25), ("Turb32_Row5_", "f64", "fast", 12), ("HornsRev1_", "f64", "fast", 6),
     ("Ablaincourt_", "f64", "basic", 25), ("Ablaincourt_", "f32", "fast", 25), ("Ablaincourt_", "f32", "basic", 10),
     ("Turb_TCRWP_", "f32", "fast", 12), ("Turb32_Row5_", "f64", "basic", 12), ("HornsRev1_", "f64", "basic", 6),
     ("HornsRev1_", "f32", "fast", 6),
@@ -77,7 +78,7 @@ def test_env_step_matches_oracle(cuda_device, name, precision, kernel, steps):
     fb.close()
 
 
-@pytest.mark.parametrize("precision,kernel", [("f64", "basic"), ("f32", "fast")])
+@pytest.mark.parametrize("precision,kernel", [("f64", "basic"), ("f64", "fast"), ("f32", "fast")])
 def test_multi_agent_constraint_discrete_and_shapers(cuda_device, precision, kernel):
     import torch
 

@@ -12,6 +12,7 @@ CASES = [  # BASELINE.json configs[1..4]: (layout, envs, precision, kernel)
     ("Ablaincourt_", 4096, "f32", "fast"),
     ("Turb16_TCRWP_", 16384, "f32", "fast"),
     ("Turb32_Row5_", 8192, "f64", "basic"),
+    ("Turb32_Row5_", 8192, "f64", "fast"),
     ("HornsRev1_", 8192, "f32", "fast"),
 ]
 

@@ -36,7 +36,7 @@ def _run(name, B, precision, kernel, seed):
 
 
 @pytest.mark.parametrize("name", CONFIG_LAYOUTS)
-@pytest.mark.parametrize("precision,kernel", [("f64", "basic"), ("f32", "basic"), ("f32", "fast")])
+@pytest.mark.parametrize("precision,kernel", [("f64", "basic"), ("f64", "fast"), ("f32", "basic"), ("f32", "fast")])
 def test_solve_matches_oracle(cuda_device, name, precision, kernel):
     B = 48
     got, order, ref, ws, wd = _run(name, B, precision, kernel, seed=3)

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwfcrl_b200.so")
-SOURCES = ["wf_api.cu", "wf_kernels.cu", "wf_fast.cu"]
+SOURCES = ["wf_api.cu", "wf_kernels.cu", "wf_fast.cu", "wf_fast64.cu"]
 HEADERS = ["wf_device.cuh", "wf_host_const.h", "gen_baked.cu", os.path.join("..", "..", "include", "wfcrl_b200.h")]
 BAKED = os.path.join(CSRC, "wf_fast_baked.inc")
 NVCC_FLAGS = [

@@ -29,6 +29,7 @@ struct WfHandle_t {
     WfConfig cfg;
     WfModel model;
     WfFastConst fast;
+    WfFastConst64 fast64;
     bool fast_baked = false;  // model constants equal the compile-time baked ones -> specialised kernel
     WfState st;
     int device = 0;
@@ -99,8 +100,6 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if (cfg->wind_veer != 0.0) return set_err(WF_ERR_INVALID, "wind_veer != 0 is not supported (case.yaml:39 uses 0)");
     if (!(cfg->yaw_lo < cfg->yaw_hi)) return set_err(WF_ERR_INVALID, "yaw bounds: need low < high (mdp.py:196)");
     if (cfg->precision != WF_PREC_F64 && cfg->precision != WF_PREC_F32) return set_err(WF_ERR_INVALID, "bad precision");
-    if (cfg->kernel == WF_KERNEL_FAST && cfg->precision != WF_PREC_F32)
-        return set_err(WF_ERR_INVALID, "WF_KERNEL_FAST requires WF_PREC_F32");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -139,6 +138,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     }
     m.xc = (xmin + xmax) / 2; m.yc = (ymin + ymax) / 2;
     build_fast_const(*cfg, &h->fast);
+    build_fast_const(*cfg, &h->fast64);
     h->fast_baked = wf_baked_matches(h->fast) && !getenv("WFCRL_B200_NO_BAKED");  // env var: force the generic kernel (tests)
 
     int rc = WF_OK;
@@ -214,7 +214,9 @@ static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float*
                        const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1) {
     if (env_count < 0) env_count = h->model.B;
     cudaError_t e;
-    if (h->cfg.kernel == WF_KERNEL_FAST)
+    if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64)
+        e = wf_launch_step_fast64(mode, h->model, h->fast64, h->st, d_mask, d_action, d_yaw, out, env_begin, env_count, st);
+    else if (h->cfg.kernel == WF_KERNEL_FAST)
         e = wf_launch_step_fast(mode, h->fast_baked, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
                                 env_count, st);
     else
@@ -414,7 +416,9 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
     CUDA_TRY(cudaSetDevice(h->device));
     cudaFuncAttributes attr;
     int ctas = 0, thr = (h->model.T + 31) / 32 * 32, sm = 0;
-    if (h->cfg.kernel == WF_KERNEL_FAST) {
+    if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64) {
+        CUDA_TRY(wf_step_fast64_attributes(h->model, &attr, &ctas, &thr, &sm));
+    } else if (h->cfg.kernel == WF_KERNEL_FAST) {
         CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->model, &attr, &ctas, &thr, &sm));
     } else {
         CUDA_TRY(wf_step_basic_attributes(h->cfg.precision, &attr, &ctas, thr));

@@ -52,32 +52,35 @@ struct WfState {
                         //         .z: first t with X[t] > x_i ; .w: first t with X[t] > x_i+15D   (T if none)
 };
 
-// Constants of the tuned FP32 kernel, precomputed on the host in FP64 (wf_api.cu: build_fast_const).
-struct WfFastConst {
-    float ratio[3];        // (Z_k / HH)^shear : U0[k] = ws * ratio[k]
-    float mean_ratio;      // Uinf = ws * mean_ratio
-    float nu4[3];          // 4 * nu_k / Uinf (independent of ws)
-    float zz[6][3];        // Z_k + c_v + NUM_EPS, vortices in FLORIS order V1..V6 (see wf_kernels.cu transverse())
-    float zz2[6][3];       // zz^2
-    float ez[6][3];        // exp(-zz^2 / eps^2)
-    float cblk[48];        // the same constants packed for the kernel's shared-memory block (see build_fast_const)
-    float a_top, a_bot, a_core;   // secondary steering: mean over the own grid of z/(2 pi r) * core per unit circulation
-    float cv[3][9], cw[3][9];     // self-induced V / W per unit (Gt, Gb, Gwr) on the own grid
-    float sv[3];                  // sum over the 9 points of cv
-    float D, inv_D, eps2, inv_eps2, inv_2pi;
-    float c_top, c_bot, c_wr;     // G_top0 = c_top*ws*ct ; G_bot0 = c_bot*ws*ct ; Gwr = c_wr*(a-a^2)*avg
-    float alpha4, beta2, ka, kb, ad, bd, dm03, e3_112, e3_13;
-    float near_c;                 // 0.501 * D * sqrt(1/2)
-    float d2_8;                   // D^2 / 8
-    float ch_const, ch_ai, ch_init, ch_down;
-    float pP3, rho_fac, ref_rho, two_D, offj[3], dz2[3];
-    float load_coef, shaper_reference;
+// Constants of the tuned warp-per-env kernels, precomputed on the host in FP64 (wf_host_const.h: build_fast_const);
+// R = R for the FP32 kernel, double for the FP64 bit-check instantiation.
+template <typename R> struct WfFastConstT {
+    R ratio[3];        // (Z_k / HH)^shear : U0[k] = ws * ratio[k]
+    R mean_ratio;      // Uinf = ws * mean_ratio
+    R nu4[3];          // 4 * nu_k / Uinf (independent of ws)
+    R zz[6][3];        // Z_k + c_v + NUM_EPS, vortices in FLORIS order V1..V6 (see wf_kernels.cu transverse())
+    R zz2[6][3];       // zz^2
+    R ez[6][3];        // exp(-zz^2 / eps^2)
+    R cblk[48];        // the same constants packed for the kernel's shared-memory block (see build_fast_const)
+    R a_top, a_bot, a_core;   // secondary steering: mean over the own grid of z/(2 pi r) * core per unit circulation
+    R cv[3][9], cw[3][9];     // self-induced V / W per unit (Gt, Gb, Gwr) on the own grid
+    R sv[3];                  // sum over the 9 points of cv
+    R D, inv_D, eps2, inv_eps2, inv_2pi;
+    R c_top, c_bot, c_wr;     // G_top0 = c_top*ws*ct ; G_bot0 = c_bot*ws*ct ; Gwr = c_wr*(a-a^2)*avg
+    R alpha4, beta2, ka, kb, ad, bd, dm03, e3_112, e3_13;
+    R near_c;                 // 0.501 * D * sqrt(1/2)
+    R d2_8;                   // D^2 / 8
+    R ch_const, ch_ai, ch_init, ch_down;
+    R pP3, rho_fac, ref_rho, two_D, offj[3], dz2[3];
+    R load_coef, shaper_reference;
     int table_len;
-    float tab_ws[64], tab_ct[64], tab_pw[64];
+    R tab_ws[64], tab_ct[64], tab_pw[64];
     unsigned char coarse[128];    // coarse[floor(x * coarse_scale)] = table interval containing that bucket's left edge
-    float coarse_scale;
+    R coarse_scale;
     int coarse_len;
 };
+typedef WfFastConstT<float> WfFastConst;
+typedef WfFastConstT<double> WfFastConst64;
 
 struct WfOutPtrs {
     void* yaw;
@@ -108,3 +111,8 @@ cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const Wf
                                 const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
 cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);
+cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                                  const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                  const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
+cudaError_t wf_step_fast64_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+                                      int* smem);

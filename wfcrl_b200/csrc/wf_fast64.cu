@@ -1,0 +1,492 @@
+// FP64 instantiation of the warp-per-env design (bit-check mode at speed): ONE WARP = ONE CTA = ONE ENVIRONMENT.
+//
+// Same structure as wf_fast.cu -- solver state in shared memory, warp-uniform source prologue, a vortex sweep over all
+// downstream targets and a compacted deficit sweep, 10 turbines x 3 lateral grid columns per pass -- but everything is
+// evaluated in double precision with the accurate CUDA math functions, and every simplification that would be visible
+// at the 1e-9 level is dropped:
+//   * positions are the FP64 rotated coordinates and the numpy-order means x_i, y_i of the geometry kernel;
+//   * the ground-mirror vortices keep their exp(-r/eps^2) core factor;
+//   * the deficit cut-off is 9.5 sigma (exp(-45) = 2.9e-20);
+//   * x-direction masks come from the geometry kernel's FP64 index table (bit-exact).
+// Algebra that only changes results at the rounding level (1e-16) is kept: exp(-(y^2+z^2)/eps^2) factorisation, paired
+// reciprocals, uR/(U0+u0) = 1/2, per-model grid integrals, sum of squares instead of the hypot chain, running maximum of
+// the wake-added TI.  Parity vs the oracle: <= 1e-9 relative (tests/test_solve_parity_gpu.py, test_env_parity_gpu.py).
+//
+// Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
+// wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
+#include "wf_device.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kDeg = 180.0 / kPi;
+constexpr double kRad = kPi / 180.0;
+constexpr double kNumEps = 0.001;
+constexpr int kTurbPerPass = 10;
+
+__device__ __forceinline__ double dclamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+__device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double* __restrict__ fp, double x, double left,
+                                           double right) {
+    const int n = fc.table_len;
+    const double x0 = fc.tab_ws[0], xn = fc.tab_ws[n - 1];
+    if (x < x0) return left;
+    if (x > xn) return right;
+    int bkt = (int)((x - x0) * fc.coarse_scale);
+    bkt = min(bkt, fc.coarse_len - 1);
+    int idx = fc.coarse[bkt];
+    while (idx + 1 < n - 1 && fc.tab_ws[idx + 1] <= x) ++idx;
+    const double xa = fc.tab_ws[idx], fa = fp[idx];
+    if (x == xa) return fa;
+    const double slope = (fp[idx + 1] - fa) / (fc.tab_ws[idx + 1] - xa);
+    return slope * (x - xa) + fa;
+}
+
+struct SmemView64 {
+    double2* vw;              // [9T] (v, w) per rotor point
+    double* wsq;              // [9T] running sum of squared deficits
+    double *xs, *ys, *xi, *yi;  // [T] sorted rotated coordinates and numpy-order grid means
+    double* tia;              // [3T]
+    double *cyaw, *syaw, *yawd;  // [T] cos / sin / degrees of the yaw (sorted order)
+    double* tifin;            // [T]
+    double* ynew;             // [T] new yaw, degrees, ORIGINAL order
+    uchar4* idx;              // [T]
+    unsigned char* ordr;      // [T]
+    unsigned char* queue;     // [T]
+};
+
+__host__ __device__ inline size_t fast64_smem_bytes(int T) {
+    size_t n = 0;
+    n += (size_t)9 * T * 16;  // vw
+    n += (size_t)9 * T * 8;   // wsq
+    n += (size_t)4 * T * 8;   // xs, ys, xi, yi
+    n += (size_t)3 * T * 8;   // tia
+    n += (size_t)5 * T * 8;   // cyaw, syaw, yawd, tifin, ynew
+    n += (size_t)T * 4;       // idx
+    n += (size_t)2 * ((T + 15) / 16 * 16);
+    return (n + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T) {
+    SmemView64 s;
+    s.vw = (double2*)base;
+    double* f = (double*)(s.vw + 9 * T);
+    s.wsq = f; f += 9 * T;
+    s.xs = f; f += T;
+    s.ys = f; f += T;
+    s.xi = f; f += T;
+    s.yi = f; f += T;
+    s.tia = f; f += 3 * T;
+    s.cyaw = f; f += T;
+    s.syaw = f; f += T;
+    s.yawd = f; f += T;
+    s.tifin = f; f += T;
+    s.ynew = f; f += T;
+    s.idx = (uchar4*)f;
+    s.ordr = (unsigned char*)(s.idx + T);
+    s.queue = s.ordr + (T + 15) / 16 * 16;
+    return s;
+}
+
+__global__ void __launch_bounds__(32, 4)
+wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, const __grid_constant__ WfFastConst64 fc,
+                      const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
+                      const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
+    const int b = blockIdx.x + env_begin;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    const int lane = threadIdx.x;
+    const size_t row = (size_t)b * T;
+    extern __shared__ __align__(16) unsigned char smem_raw64[];
+    const SmemView64 sm = carve64(smem_raw64, T);
+
+    // ---- env prologue on the ORIGINAL turbine order (mdp.py:291-319, simple_env.py:64-72) -------------------------
+    int nm = 0;
+    if (mode == WF_MODE_ENV) nm = s.num_moves[b] + 1;
+    for (int tt = lane; tt < T; tt += 32) {
+        double ynew;
+        if (mode == WF_MODE_ENV) {
+            float a = action[row + tt];
+            const float acc = s.acc[row + tt];
+            const float acc_c = (m.multi_agent && tt != T - 1) ? s.acc_prev[row + tt] : acc;
+            const float frac = __fdiv_rn(__fdiv_rn(__fdiv_rn(acc_c, m.rate_f), (float)nm), m.dt_f);
+            if (frac >= 0.1f) a = 0.0f;
+            if (m.continuous) a = fminf(fmaxf(a, -m.yaw_step_f), m.yaw_step_f);
+            else a = __fmul_rn(__fsub_rn(a, 1.0f), m.yaw_step_f);
+            const float y0 = fminf(fmaxf((float)s.yaw[row + tt], m.yaw_lo_f), m.yaw_hi_f);
+            const float y1 = fminf(fmaxf(__fadd_rn(y0, a), m.yaw_lo_f), m.yaw_hi_f);
+            s.acc_prev[row + tt] = acc;
+            s.acc[row + tt] = __fadd_rn(acc, fabsf(a));
+            ynew = (double)y1;
+            s.yaw[row + tt] = ynew;
+        } else if (mode == WF_MODE_INTERFACE && yaw_cmd) {
+            ynew = yaw_cmd[row + tt];
+            s.yaw[row + tt] = ynew;
+        } else {
+            ynew = s.yaw[row + tt];
+        }
+        sm.ynew[tt] = ynew;
+        sm.xs[tt] = s.xs[row + tt];
+        sm.ys[tt] = s.ys[row + tt];
+        sm.xi[tt] = s.xi[row + tt];
+        sm.yi[tt] = s.yi[row + tt];
+        sm.idx[tt] = s.idx[row + tt];
+        sm.ordr[tt] = (unsigned char)s.order[row + tt];
+    }
+    for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.0; sm.vw[q] = make_double2(0.0, 0.0); }
+    for (int q = lane; q < 3 * T; q += 32) sm.tia[q] = 0.0;
+    __syncwarp();
+    for (int tt = lane; tt < T; tt += 32) {
+        const double yd = sm.ynew[sm.ordr[tt]];
+        double sy, cy;
+        sincos(yd * kRad, &sy, &cy);
+        sm.yawd[tt] = yd;
+        sm.cyaw[tt] = cy;
+        sm.syaw[tt] = sy;
+    }
+    const double ws = s.ws[b], wd = s.wd[b];
+    const double I0 = s.ti_amb[b];
+    const double I02 = I0 * I0;
+    const double I0p = pow(I0, fc.ch_init);
+    const double U0a = ws * fc.ratio[0], U0b = ws * fc.ratio[1], U0c = ws * fc.ratio[2];
+    const double D = fc.D;
+    __syncwarp();
+
+    const int g = lane / 3, j = lane - 3 * g;
+    const bool lane_ok = lane < 3 * kTurbPerPass;
+    const double offj = (j == 0) ? fc.offj[0] : ((j == 1) ? fc.offj[1] : fc.offj[2]);
+    const int pl = lane & 15;
+    const bool pv = pl < 9;
+    const int plc = pv ? pl : 0;
+    const double U0p = (plc % 3 == 0) ? U0a : ((plc % 3 == 1) ? U0b : U0c);
+    const double cvl0 = fc.cv[0][plc], cvl1 = fc.cv[1][plc], cvl2 = fc.cv[2][plc];
+    const double cwl0 = fc.cw[0][plc], cwl1 = fc.cw[1][plc], cwl2 = fc.cw[2][plc];
+    const double c_dec = fc.eps2 * fc.inv_2pi;
+    const double eps2 = fc.eps2;
+
+    for (int i = 0; i < T; ++i) {
+        // ===== source prologue =====
+        double su3, sv, sw, vq, wwq;
+        {
+            const double wq = sm.wsq[9 * i + plc];
+            const double2 vw0 = sm.vw[9 * i + plc];
+            vq = vw0.x;
+            wwq = vw0.y;
+            const double u = U0p - sqrt(wq);
+            su3 = pv ? u * u * u : 0.0;
+            sv = pv ? vq : 0.0;
+            sw = pv ? wwq : 0.0;
+#pragma unroll
+            for (int sft = 8; sft > 0; sft >>= 1) {
+                su3 += __shfl_xor_sync(0xffffffffu, su3, sft);
+                sv += __shfl_xor_sync(0xffffffffu, sv, sft);
+                sw += __shfl_xor_sync(0xffffffffu, sw, sft);
+            }
+        }
+        const double avg = cbrt(su3 / 9.0);
+        const double ct_raw = dclamp(interp_d(fc, fc.tab_ct, avg, 0.0001, 0.9999), 0.0001, 0.9999);
+        const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.yawd[i];
+        const double ct = ct_raw * cy;
+        const double a = 0.5 / cy * (1.0 - sqrt(1.0 - ct * cy));
+        const double Gtop0 = fc.c_top * ws * ct, Gbot0 = fc.c_bot * ws * ct;
+        const double Gwr = fc.c_wr * (a - a * a) * avg;
+        const double Gt = sy * cy * Gtop0, Gb = -(sy * cy * Gbot0);
+
+        // A.5 secondary steering through the per-model grid integrals
+        double val = 2.0 * (sv / 9.0 - Gwr * fc.a_core) / (Gtop0 * fc.a_top - Gbot0 * fc.a_bot);
+        val = dclamp(val, -1.0, 1.0);
+        const double g_deg = -(yd + kDeg * (0.5 * asin(val)));  // minus the effective yaw, degrees
+        const double g_rad = g_deg * kRad;
+        const double cg = cos(g_rad);
+
+        // A.6 deflection scalars
+        const double sq1ct = sqrt(1.0 - ct);
+        const double sqcg = sqrt(1.0 - ct * cg);
+        const double sz0d = 0.5 * D * sqrt((1.0 + sqcg) / (2.0 * (1.0 + sq1ct)));
+        const double sy0d = sz0d * cg;
+        const double C0 = 1.0 - sq1ct;
+        const double M0 = C0 * (2.0 - C0);
+        const double E0 = C0 * C0 - fc.e3_112 * C0 + fc.e3_13;
+        const double th = fc.dm03 * g_rad / cg * (1.0 - sqcg);
+        const double sM0 = sqrt(M0);
+        const double tan_th = tan(th);
+        const double Kc = th * E0 / 5.2 * sqrt(sy0d * sz0d / M0);
+        const double A_ln = (1.6 + sM0) / (1.6 - sM0);
+        const double inv_s0d = 1.0 / (sy0d * sz0d);
+
+        const double ta0 = sm.tia[3 * i], ta1 = sm.tia[3 * i + 1], ta2 = sm.tia[3 * i + 2];
+        const double tp0 = sqrt(ta0 * ta0 + I02), tp1 = sqrt(ta1 * ta1 + I02), tp2 = sqrt(ta2 * ta2 + I02);
+        const double tpre = (j == 0) ? tp0 : ((j == 1) ? tp1 : tp2);
+        const double beta_term = fc.beta2 * (1.0 - sq1ct);
+        const double x0d = D * cg * (1.0 + sqcg) / (1.4142135623730951 * (fc.alpha4 * tpre + beta_term));
+        const double kyd = fc.ka * tpre + fc.kb;
+        const double delta0 = tan_th * x0d;
+        const double Kck = Kc / kyd;
+
+        // own transverse velocities + yaw-added recovery (in-place TI update)
+        const uchar4 ix = sm.idx[i];
+        const bool self_on = (int)ix.x <= i;
+        double sumV = sv, sumW = sw;
+        if (self_on) {
+            sumV += Gt * fc.sv[0] + Gb * fc.sv[1] + Gwr * fc.sv[2];
+            const double Vs = Gt * cvl0 + Gb * cvl1 + Gwr * cvl2;
+            const double Ws = fmax(Gt * cwl0 + Gb * cwl1 + Gwr * cwl2, 0.0);
+            double rw = pv ? Ws : 0.0;
+#pragma unroll
+            for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
+            sumW += rw;
+            __syncwarp();
+            if (lane < 9) sm.vw[9 * i + lane] = make_double2(vq + Vs, wwq + Ws);
+        }
+        const double aI = avg * tp0;
+        const double kk2 = 3.0 * aI * aI;
+        const double v_term = sumV / 9.0, w_term = sumW / 9.0;
+        const double k_total = 0.5 * (kk2 + v_term * v_term + w_term * w_term);
+        const double I_mix = sqrt((2.0 / 3.0) * k_total) / avg - tp0;
+        const double tq0 = tp0 + 2.0 * I_mix, tq1 = tp1 + 2.0 * I_mix, tq2 = tp2 + 2.0 * I_mix;
+        if (lane == 0) sm.tifin[i] = ((tq0 + tq1) + tq2) / 3.0;
+        const double tpost = (j == 0) ? tq0 : ((j == 1) ? tq1 : tq2);
+
+        // A.8 velocity-model scalars with the updated TI
+        const double x0v = D * cy * (1.0 + sq1ct) / (1.4142135623730951 * (fc.alpha4 * tpost + beta_term));
+        const double kyv = fc.ka * tpost + fc.kb;
+        const double sz0v = fc.near_c * (0.5 / 0.501);
+        const double sy0v = sz0v * cy;
+        const double near_s = fc.near_c * sqrt(ct);
+        const double ctc = ct * cy * fc.d2_8;
+        const double watK = fc.ch_const * pow(a, fc.ch_ai) * I0p;
+
+        const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
+        const double x_i = sm.xi[i], y_i = sm.yi[i];
+
+        constexpr double kCut = 9.5;
+        const double reach1 = kCut * kyv;
+        const double reach0 = kCut * fmax(near_s, sy0v) + fabs(delta0) + fabs(Kck) * log(A_ln);
+
+        // ===== V sweep =====
+        int qn = 0;
+        for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
+            const int tr = t0 + g;
+            const bool active = lane_ok && tr < T && tr != i;
+            const int t = min(tr, T - 1);
+            const double dx = sm.xs[t] - x_i;
+            const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+
+            const bool need = active && (t >= near_i) && (fabs(dyc) < reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad));
+            const unsigned nb = __ballot_sync(0xffffffffu, need);
+            const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
+            const unsigned lb = __ballot_sync(0xffffffffu, leader);
+            if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
+            qn += __popc(lb);
+
+            const double yL = dyc + kNumEps;
+            const double q = yL * yL;
+            const double E = exp(-q * fc.inv_eps2);
+            double Vk[3], Wk[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                // pairs (real a, ground mirror b): (0,2) top, (1,3) bottom, (4,5) wake rotation
+                const double r0 = q + fc.zz2[0][k], r2 = q + fc.zz2[2][k], r1 = q + fc.zz2[1][k], r3 = q + fc.zz2[3][k];
+                const double r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
+                const double g0 = Gt / (r0 * r2), g1 = Gb / (r1 * r3), g4 = Gwr / (r4 * r5);
+                const double Xa0 = (1.0 - E * fc.ez[0][k]) * r2, Xb0 = (1.0 - E * fc.ez[2][k]) * r0;
+                const double Xa1 = (1.0 - E * fc.ez[1][k]) * r3, Xb1 = (1.0 - E * fc.ez[3][k]) * r1;
+                const double Xa4 = (1.0 - E * fc.ez[4][k]) * r5, Xb4 = (1.0 - E * fc.ez[5][k]) * r4;
+                const double SV = g0 * (fc.zz[0][k] * Xa0 - fc.zz[2][k] * Xb0) + g1 * (fc.zz[1][k] * Xa1 - fc.zz[3][k] * Xb1) +
+                                  g4 * (fc.zz[4][k] * Xa4 - fc.zz[5][k] * Xb4);
+                const double SW = g0 * (Xa0 - Xb0) + g1 * (Xa1 - Xb1) + g4 * (Xa4 - Xb4);
+                const double dec = c_dec / (fc.nu4[k] * dx + eps2);
+                Vk[k] = SV * dec;
+                Wk[k] = fmax(SW * (-yL * dec), 0.0);
+            }
+            if (active) {
+                const int qb = 9 * t + 3 * j;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double2 o = sm.vw[qb + k];
+                    sm.vw[qb + k] = make_double2(o.x + Vk[k], o.y + Wk[k]);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ===== D sweep =====
+        for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
+            const int e = q0 + g;
+            const bool active = lane_ok && e < qn;
+            const int t = sm.queue[min(e, qn - 1)];
+            const double dx = sm.xs[t] - x_i;
+            const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+            const double lin = fc.bd * dx + fc.ad;
+            double defl;
+            if (dx <= x0d) {
+                defl = dx / x0d * delta0 + lin;
+            } else {
+                const double dd = dx - x0d;
+                const double sgy = kyd * dd + sy0d, sgz = kyd * dd + sz0d;
+                const double sq = sqrt(sgy * sgz * inv_s0d);
+                const double L = log(A_ln * (1.6 * sq - sM0) / (1.6 * sq + sM0));
+                defl = delta0 + Kck * L + lin;
+            }
+            double base, ek;
+            {
+                const bool far = dx >= x0v;
+                const double dd = dx - x0v;
+                const double up = dx / x0v, down = (x0v - dx) / x0v;
+                const double sgy = far ? kyv * dd + sy0v : down * near_s + up * sy0v;
+                const double sgz = far ? kyv * dd + sz0v : down * near_s + up * sz0v;
+                const double dy = (dyc - defl) / sgy;
+                const double dcl = dclamp(1.0 - ctc / (sgy * sgz), 0.0, 1.0);
+                base = (1.0 - sqrt(dcl)) * exp(-0.5 * dy * dy);
+                ek = exp(-0.5 * fc.dz2[0] / (sgz * sgz));
+            }
+            const double be = base * ek;
+            const double dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
+            int c = 0;
+            if (active) {
+                c = (dU0 > 0.05) + (dU1 > 0.05) + (dU2 > 0.05);
+                const int qb = 9 * t + 3 * j;
+                sm.wsq[qb] += dU0 * dU0;
+                sm.wsq[qb + 1] += dU1 * dU1;
+                sm.wsq[qb + 2] += dU2 * dU2;
+            }
+            const int gb = 3 * g;
+            const int c_tot = __shfl_sync(0xffffffffu, c, gb & 31) + __shfl_sync(0xffffffffu, c, (gb + 1) & 31) +
+                              __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
+            if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabs(dyc) < fc.two_D) {
+                const double dxp = dx + ((dx <= 0.1) ? 1.0 : 0.0);
+                const double wat = watK * pow(dxp / D, fc.ch_down);
+                const double ta = ((double)c_tot / 9.0) * wat;
+                sm.tia[3 * t + j] = fmax(sm.tia[3 * t + j], ta);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    const bool env = (mode != WF_MODE_INTERFACE);
+    double rsum_p = 0.0, rsum_l = 0.0;
+    for (int tt = lane; tt < T; tt += 32) {
+        double u[9], vv[9], ww[9], c3[9], dd[9];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            const double U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
+            u[p] = U0k - sqrt(sm.wsq[9 * tt + p]);
+            const double2 vwp = sm.vw[9 * tt + p];
+            vv[p] = vwp.x;
+            ww[p] = vwp.y;
+            c3[p] = u[p] * u[p] * u[p];
+            dd[p] = wd - kDeg * atan2(vv[p], u[p]);
+        }
+        auto sum9 = [](const double* p) {
+            return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
+        };
+        const double avg = cbrt(sum9(c3) / 9.0);
+        const double veff = fc.rho_fac * avg * pow(sm.cyaw[tt], fc.pP3);
+        const double pw = interp_d(fc, fc.tab_pw, veff, 0.0, 0.0) * fc.ref_rho;  // [W]
+        double wsl = avg;
+        double wdl = sum9(dd) / 9.0;
+        double sd[3];
+        {
+            const double* arrs[3] = {u, vv, ww};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const double mu = sum9(arrs[q]) / 9.0;
+                double d2[9];
+#pragma unroll
+                for (int p = 0; p < 9; ++p) { const double e = arrs[q][p] - mu; d2[p] = e * e; }
+                sd[q] = sqrt(sum9(d2) / 9.0);
+            }
+        }
+        double loads[4] = {sm.tifin[tt], sd[0], sd[1], sd[2]};
+        double p_out;
+        if (env) {
+            p_out = pw / 1e6;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                loads[q] = (loads[q] * 1e7) / 1e7;
+                rsum_l += fabs(loads[q]);
+            }
+            rsum_p += p_out;
+        } else {
+            p_out = pw;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) loads[q] = loads[q] * 1e7;
+        }
+        const int orig = sm.ordr[tt];
+        double yv = sm.ynew[orig];
+        if (mode == WF_MODE_WARMUP) {
+            wsl = dclamp(wsl, 3.0, 28.0);
+            wdl = dclamp(wdl, 0.0, 360.0);
+            yv = dclamp(yv, (double)m.yaw_lo_f, (double)m.yaw_hi_f);
+        }
+        const size_t o = row + orig;
+        if (out.yaw) ((double*)out.yaw)[o] = yv;
+        if (out.wind_speed) ((double*)out.wind_speed)[o] = wsl;
+        if (out.wind_direction) ((double*)out.wind_direction)[o] = wdl;
+        if (out.power) ((double*)out.power)[o] = p_out;
+        if (out.load) {
+            double* Lp = (double*)out.load + 4 * o;
+            Lp[0] = loads[0]; Lp[1] = loads[1]; Lp[2] = loads[2]; Lp[3] = loads[3];
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        rsum_p += __shfl_xor_sync(0xffffffffu, rsum_p, sft);
+        rsum_l += __shfl_xor_sync(0xffffffffu, rsum_l, sft);
+    }
+    if (lane == 0) {
+        const int it = s.num_iter[b] + 1;
+        s.num_iter[b] = it;
+        if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
+        double fw0 = ws, fw1 = wd;
+        if (mode == WF_MODE_WARMUP) { fw0 = dclamp(fw0, 3.0, 28.0); fw1 = dclamp(fw1, 0.0, 360.0); }
+        if (out.freewind) { ((double*)out.freewind)[2 * b] = fw0; ((double*)out.freewind)[2 * b + 1] = fw1; }
+        if (mode == WF_MODE_ENV) {
+            s.num_moves[b] = nm;
+            const double wn = s.ws_norm[b];
+            double reward = rsum_p * 1e3 / (wn * wn * wn) / T - m.load_coef * (rsum_l / (4.0 * T));
+            if (m.shaper == 1) {
+                reward = (reward - m.shaper_reference) / m.shaper_reference;
+            } else if (m.shaper == 2) {
+                const double ref = s.shaper_ref[b];
+                const double shaped = (ref == 0.0) ? 0.0 : (reward - ref) / ref;
+                s.shaper_ref[b] = reward;
+                reward = shaped;
+            }
+            if (out.reward) ((double*)out.reward)[b] = reward;
+            s.ws_norm[b] = ws;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                                  const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
+                                  const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
+    const size_t smem = fast64_smem_bytes(m.T);
+    cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    wf_step_fast64_kernel<<<env_count, 32, smem, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_step_fast64_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+                                      int* smem) {
+    *threads = 32;
+    *smem = (int)fast64_smem_bytes(m.T);
+    cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(attr, wf_step_fast64_kernel);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast64_kernel, 32, *smem);
+}

@@ -45,7 +45,7 @@ static inline void wf_fill_default_config(WfConfig* c) {
     }
 
 // Host-side (FP64) precomputation of the tuned FP32 kernel's per-model constants.
-static inline void build_fast_const(const WfConfig& c, WfFastConst* f) {
+template <typename R> static inline void build_fast_const(const WfConfig& c, WfFastConstT<R>* f) {
     memset(f, 0, sizeof(*f));
     const double PI = 3.141592653589793, NUM_EPS = 0.001;
     const double D = c.rotor_diameter, HH = c.hub_height, eps = 0.2 * D, eps2 = eps * eps, off = 0.5 * D / 2;
@@ -56,30 +56,30 @@ static inline void build_fast_const(const WfConfig& c, WfFastConst* f) {
         rsum += ratio[k];
     }
     const double mean_ratio = rsum / 3.0;
-    f->mean_ratio = (float)mean_ratio;
+    f->mean_ratio = (R)mean_ratio;
     const double zc[6] = {-(HH + D / 2), -(HH - D / 2), (HH + D / 2), (HH - D / 2), -HH, HH};
     double zz[6][3];
     for (int k = 0; k < 3; ++k) {
-        f->ratio[k] = (float)ratio[k];
+        f->ratio[k] = (R)ratio[k];
         const double dU = c.wind_shear * pow(1.0 / HH, c.wind_shear) * pow(Z[k], c.wind_shear - 1.0);  // per unit ws
         const double lmda = D / 8, kappa = 0.41;
         const double lm = kappa * Z[k] / (1 + kappa * Z[k] / lmda);
-        f->nu4[k] = (float)(4 * lm * lm * fabs(dU) / mean_ratio);
+        f->nu4[k] = (R)(4 * lm * lm * fabs(dU) / mean_ratio);
         for (int q = 0; q < 6; ++q) {
             zz[q][k] = (Z[k] + zc[q]) + NUM_EPS;
-            f->zz[q][k] = (float)zz[q][k];
-            f->zz2[q][k] = (float)(zz[q][k] * zz[q][k]);
-            f->ez[q][k] = (float)exp(-zz[q][k] * zz[q][k] / eps2);
+            f->zz[q][k] = (R)zz[q][k];
+            f->zz2[q][k] = (R)(zz[q][k] * zz[q][k]);
+            f->ez[q][k] = (R)exp(-zz[q][k] * zz[q][k] / eps2);
         }
-        f->dz2[k] = (float)(((k - 1) * off) * ((k - 1) * off));
-        f->offj[k] = (float)((k - 1) * off);
+        f->dz2[k] = (R)(((k - 1) * off) * ((k - 1) * off));
+        f->offj[k] = (R)((k - 1) * off);
     }
     // packed block: per k four float4 = (zz2_top, zz2_topmirror, zz2_bot, zz2_botmirror) (zz2_core, zz2_coremirror,
     // ez_top, ez_bot) (ez_core, zz_top, zz_topmirror, zz_bot) (zz_botmirror, zz_core, zz_coremirror, nu4).
     // Vortex order in zz[][]: 0 top, 1 bottom, 2 top mirror, 3 bottom mirror, 4 core, 5 core mirror.  The mirror vortices'
     // cores are taken as 1 (exp(-zz^2/eps^2) <= 1.1e-5 for them).
     for (int k = 0; k < 3; ++k) {
-        float* c = f->cblk + 16 * k;
+        R* c = f->cblk + 16 * k;
         c[0] = f->zz2[0][k]; c[1] = f->zz2[2][k]; c[2] = f->zz2[1][k]; c[3] = f->zz2[3][k];
         c[4] = f->zz2[4][k]; c[5] = f->zz2[5][k]; c[6] = f->ez[0][k]; c[7] = f->ez[1][k];
         c[8] = f->ez[4][k]; c[9] = f->zz[0][k]; c[10] = f->zz[2][k]; c[11] = f->zz[1][k];
@@ -101,40 +101,40 @@ static inline void build_fast_const(const WfConfig& c, WfFastConst* f) {
                               zz[4][k] * fq[4] - zz[5][k] * fq[5]};
         const double cw[3] = {-yL * (fq[0] - fq[2]), -yL * (fq[1] - fq[3]), -yL * (fq[4] - fq[5])};
         for (int v = 0; v < 3; ++v) {
-            f->cv[v][p] = (float)cv[v];
-            f->cw[v][p] = (float)cw[v];
+            f->cv[v][p] = (R)cv[v];
+            f->cw[v][p] = (R)cw[v];
             sv[v] += cv[v];
         }
     }
-    f->a_top = (float)a_top; f->a_bot = (float)a_bot; f->a_core = (float)a_core;
-    for (int v = 0; v < 3; ++v) f->sv[v] = (float)sv[v];
-    f->D = (float)D; f->inv_D = (float)(1.0 / D); f->eps2 = (float)eps2; f->inv_eps2 = (float)(1.0 / eps2);
-    f->inv_2pi = (float)(1.0 / (2 * PI));
+    f->a_top = (R)a_top; f->a_bot = (R)a_bot; f->a_core = (R)a_core;
+    for (int v = 0; v < 3; ++v) f->sv[v] = (R)sv[v];
+    f->D = (R)D; f->inv_D = (R)(1.0 / D); f->eps2 = (R)eps2; f->inv_eps2 = (R)(1.0 / eps2);
+    f->inv_2pi = (R)(1.0 / (2 * PI));
     const double vel_top = pow((HH + D / 2) / HH, c.wind_shear), vel_bot = pow((HH - D / 2) / HH, c.wind_shear);
-    f->c_top = (float)((PI / 8) * D * vel_top * mean_ratio);
-    f->c_bot = (float)((PI / 8) * D * vel_bot * mean_ratio);
-    f->c_wr = (float)(0.25 * 2 * PI * D / c.tsr);
-    f->alpha4 = (float)(4 * c.alpha); f->beta2 = (float)(2 * c.beta); f->ka = (float)c.ka; f->kb = (float)c.kb;
-    f->ad = (float)c.ad; f->bd = (float)c.bd; f->dm03 = (float)(0.3 * c.dm);
-    f->e3_112 = (float)(3 * exp(1.0 / 12.0)); f->e3_13 = (float)(3 * exp(1.0 / 3.0));
-    f->near_c = (float)(0.501 * D * sqrt(0.5));
-    f->d2_8 = (float)(D * D / 8.0);
-    f->ch_const = (float)c.ch_constant; f->ch_ai = (float)c.ch_ai; f->ch_init = (float)c.ch_initial;
-    f->ch_down = (float)c.ch_downstream;
-    f->pP3 = (float)(c.pP / 3.0); f->rho_fac = (float)cbrt(c.air_density / c.ref_density_cp_ct);
-    f->ref_rho = (float)c.ref_density_cp_ct; f->two_D = (float)(2 * D);
-    f->load_coef = (float)c.load_coef; f->shaper_reference = (float)c.shaper_reference;
+    f->c_top = (R)((PI / 8) * D * vel_top * mean_ratio);
+    f->c_bot = (R)((PI / 8) * D * vel_bot * mean_ratio);
+    f->c_wr = (R)(0.25 * 2 * PI * D / c.tsr);
+    f->alpha4 = (R)(4 * c.alpha); f->beta2 = (R)(2 * c.beta); f->ka = (R)c.ka; f->kb = (R)c.kb;
+    f->ad = (R)c.ad; f->bd = (R)c.bd; f->dm03 = (R)(0.3 * c.dm);
+    f->e3_112 = (R)(3 * exp(1.0 / 12.0)); f->e3_13 = (R)(3 * exp(1.0 / 3.0));
+    f->near_c = (R)(0.501 * D * sqrt(0.5));
+    f->d2_8 = (R)(D * D / 8.0);
+    f->ch_const = (R)c.ch_constant; f->ch_ai = (R)c.ch_ai; f->ch_init = (R)c.ch_initial;
+    f->ch_down = (R)c.ch_downstream;
+    f->pP3 = (R)(c.pP / 3.0); f->rho_fac = (R)cbrt(c.air_density / c.ref_density_cp_ct);
+    f->ref_rho = (R)c.ref_density_cp_ct; f->two_D = (R)(2 * D);
+    f->load_coef = (R)c.load_coef; f->shaper_reference = (R)c.shaper_reference;
     const int n = c.table_len;
     f->table_len = n;
     const double area = PI * pow(D / 2.0, 2.0);
     for (int i = 0; i < n; ++i) {
-        f->tab_ws[i] = (float)c.table_ws[i];
-        f->tab_ct[i] = (float)c.table_ct[i];
-        f->tab_pw[i] = (float)(0.5 * area * c.table_cp[i] * c.generator_efficiency * pow(c.table_ws[i], 3.0));
+        f->tab_ws[i] = (R)c.table_ws[i];
+        f->tab_ct[i] = (R)c.table_ct[i];
+        f->tab_pw[i] = (R)(0.5 * area * c.table_cp[i] * c.generator_efficiency * pow(c.table_ws[i], 3.0));
     }
     f->coarse_len = 128;
     const double span = c.table_ws[n - 1] - c.table_ws[0];
-    f->coarse_scale = (float)(128.0 / span);
+    f->coarse_scale = (R)(128.0 / span);
     for (int bkt = 0; bkt < 128; ++bkt) {
         // conservative (slightly early) left edge so that float rounding of the bucket index can never skip a node
         const double left = c.table_ws[0] + (bkt - 0.01) * span / 128.0;

@@ -60,7 +60,7 @@ class VecWindFarmEnv:
         if code is None:
             raise ValueError("the batched path supports DoNothingReward, ReferencePercentage and StepPercentage")
         precision = {"fp32": "f32", "fp64": "f64"}.get(precision, precision)
-        kernel = kernel or ("fast" if precision == "f32" else "basic")
+        kernel = kernel or "fast"  # warp-per-env kernels: FP32 fast mode or its FP64 instantiation (bit-check mode)
         self.precision = precision
         self.exact_host_trig = (precision == "f64") if exact_host_trig is None else exact_host_trig
         self.backend = FlorisBatch(case["xcoords"], case["ycoords"], self.num_envs, device=device, precision=precision,
