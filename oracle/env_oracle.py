@@ -371,7 +371,7 @@ class MAEnvOracle:
             joint = {c: np.zeros(self.num_turbines, dtype=np.float32) for c in self.mdp.controls}
             for j, (_a, act) in enumerate(self.actions.items()):
                 for c in act:
-                    joint[c][j] = act[c][:]
+                    joint[c][j] = np.asarray(act[c]).reshape(-1)[0]  # reference: joint_action[control][j] = action[control][:]
             next_state, powers, loads, truncated = self.mdp.take_action(self._state, joint)
             normalized = powers * 1e3 / (self._state["freewind_measurements"][0] ** 3)
             load_penalty = np.mean(np.abs(loads)) if loads is not None else 0
