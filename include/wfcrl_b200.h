@@ -119,6 +119,7 @@ int wf_destroy(WfHandle h);
  *   h_ws, h_wd: HOST double [n] wind speed [m/s] and direction [deg] (wd is reduced % 360 as interface.py:664)
  *   h_cos, h_sin: HOST double [n] or NULL.  When given they are used as cosd/sind of the wind deviation from west
  *                 instead of the device's own FP64 cos/sin (bit-exact geometry vs a host reference).
+ * Synchronous: the stream is synchronised before returning (host arrays may be freed; resets are rare).
  */
 int wf_reset(WfHandle h, const int32_t* h_env_ids, int32_t n, const double* h_ws, const double* h_wd,
              const double* h_cos, const double* h_sin, int32_t warmup_solves, const WfStepOut* out, void* stream);

@@ -248,7 +248,6 @@ int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const 
     if (!ids && n != B) return set_err(WF_ERR_INVALID, "h_env_ids == NULL requires n == num_envs");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaStreamSynchronize(st));  // the pinned staging below may still be in flight from a previous reset
     memset(h->h_mask, 0, B);
     for (int k = 0; k < n; ++k) {
         const int b = ids ? ids[k] : k;
@@ -267,6 +266,7 @@ int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const 
     h->launches += 2;
     for (int k = 0; k < warmup; ++k)
         TRY(launch_step(h, WF_MODE_WARMUP, h->d_mask, nullptr, nullptr, to_ptrs(out), st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // the handle-owned pinned staging is reusable when this call returns
     return WF_OK;
 }
 
