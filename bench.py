@@ -53,7 +53,8 @@ def _ncu_traffic(kernel: str):
         with open(path) as fp:
             rec = json.load(fp)[kernel]
         return {"bytes_per_launch": rec["dram_bytes_read"] + rec["dram_bytes_write"], "source": rec["source"],
-                "algorithmic_bytes_per_launch": rec.get("algorithmic_bytes")}
+                "algorithmic_bytes_per_launch": rec.get("algorithmic_bytes"),
+                "warp_instructions_per_env_step": rec.get("warp_instructions_per_env_step")}
     except Exception:
         return None
 
@@ -381,8 +382,17 @@ def run_ours(args):
                     "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
             "traffic": _ncu_traffic(args.kernel),
             "avg_launch_ms": total_ms / max(launches, 1),
+            "issue_slots": None,
             "occupancy": info,
         }
+        tr = roofline["traffic"]
+        if tr and tr.get("warp_instructions_per_env_step") and precision == "f32" and T == 80:
+            # honest counterpart of the canonical fraction: instructions ACTUALLY issued (ncu count, committed) per second
+            # over the issue-slot peak (4 warp-instructions / clk / SM)
+            wi = tr["warp_instructions_per_env_step"]
+            roofline["issue_slots"] = {"warp_instr_per_env_step": wi, "achieved_G_per_s": per_gpu * wi / 1e9,
+                                       "peak_G_per_s": info["sm_count"] * 4 * sm_max_mhz * 1e6 / 1e9,
+                                       "frac": per_gpu * wi / (info["sm_count"] * 4 * sm_max_mhz * 1e6)}
         line = {
             "metric": "Floris env-steps/sec (HornsRev1)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,

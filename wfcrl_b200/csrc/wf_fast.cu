@@ -38,6 +38,10 @@ constexpr int kTurbPerPass = 10;
 #define WF_FAST_UNROLL_V 2  // two V-sweep passes in flight per warp (ILP); measured +3.5 % on B200
 #endif
 #define WF_UNROLL_V WF_PRAGMA_UNROLL_(WF_FAST_UNROLL_V)
+#ifndef WF_FAST_UNROLL_D
+#define WF_FAST_UNROLL_D 1
+#endif
+#define WF_UNROLL_D WF_PRAGMA_UNROLL_(WF_FAST_UNROLL_D)
 #ifndef WF_FAST_MINB
 #define WF_FAST_MINB 12  // lower bound on resident env-CTAs per SM for the register allocator (16 are reached)
 #endif
@@ -360,6 +364,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         __syncwarp();
 
         // ===== D sweep: deflection + Gaussian deficit + wake-added TI, only on the queued targets =====
+        WF_UNROLL_D
         for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
             const int e = q0 + g;
             const bool active = lane_ok && e < qn;
