@@ -211,3 +211,20 @@ def test_sharded_batches_equal_single_batch(cuda_device):
     full.close()
     for *_x, e in shards:
         e.close()
+
+
+def test_make_vec_sampled_turbulence_intensity(cuda_device):
+    """BASELINE configs[2] flavour: TI sampled per env at reset; start observation matches the oracle run with that TI."""
+    from wfcrl_b200 import environments as envs
+
+    B = 5
+    env = envs.make_vec("Turb16_TCRWP_Floris", B, precision="f64", max_num_steps=10, turbulence_intensity_range=(0.04, 0.12))
+    obs = env.reset(seed=50)
+    ti = env.backend.get_state("ti_ambient")
+    assert np.all((ti >= 0.04) & (ti <= 0.12)) and len(np.unique(ti)) == B
+    lx, ly = layout("Turb16_TCRWP_")
+    fw = obs["freewind_measurements"].cpu().numpy()
+    for b in range(B):
+        ref = c_oracle.solve(lx, ly, fw[b, 0], fw[b, 1], np.zeros(16), ti_ambient=ti[b])
+        assert np.allclose(obs["wind_speed"][b].cpu().numpy(), np.clip(ref.ws_local, 3, 28), rtol=1e-9)
+    env.close()

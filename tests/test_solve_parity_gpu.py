@@ -97,3 +97,35 @@ def test_generic_fast_kernel_matches_specialised(cuda_device, monkeypatch):
         fb.close()
     for k in ("power", "wind_speed", "wind_direction", "load"):
         assert torch.allclose(outs[0][k], outs[1][k], rtol=2e-6, atol=1e-6), k
+
+
+@pytest.mark.parametrize("precision,kernel", [("f64", "basic"), ("f64", "fast"), ("f32", "fast")])
+def test_sampled_turbulence_intensity_per_env(cuda_device, precision, kernel):
+    """BASELINE.json configs[2]: wind speed / direction / TI sampled per env (TI ~ U(0.04, 0.12) is an extension of the
+    reference, whose case.yaml fixes 0.06): the per-env ambient TI must reach every place FLORIS uses it."""
+    import torch
+
+    from oracle import c_oracle
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb16_TCRWP_")
+    B, T = 24, len(lx)
+    ws, wd = sample_winds(B, 12)
+    rng = np.random.default_rng(13)
+    ti = rng.uniform(0.04, 0.12, B)
+    yaw = rng.uniform(-30, 30, (B, T)).astype(np.float32).astype(np.float64)
+    fb = FlorisBatch(lx, ly, B, precision=precision, kernel=kernel, max_iter=10)
+    fb.reset(ws, wd, host_trig=True, warmup_solves=0)
+    fb.set_turbulence_intensity(torch.as_tensor(ti, device="cuda"))
+    out = fb.update_command(torch.as_tensor(yaw, device="cuda"))
+    torch.cuda.synchronize()
+    p = out["power"].double().cpu().numpy()
+    tiout = out["load"].double().cpu().numpy()[..., 0] / 1e7
+    c, s = host_trig(wd)
+    tol = TOL[precision]
+    for b in range(B):
+        ref = c_oracle.solve(lx, ly, ws[b], wd[b], yaw[b], cs=(c[b], s[b]), ti_ambient=ti[b])
+        assert rel_err(p[b], ref.power_W, 1.0) <= tol, (b, precision)
+        assert rel_err(tiout[b], ref.ti, 1e-3) <= max(tol, 1e-9)
+    assert np.allclose(fb.get_state("ti_ambient"), ti)
+    fb.close()

@@ -34,7 +34,8 @@ class VecWindFarmEnv:
                  kernel: Optional[str] = None, controls: Optional[dict] = None, continuous_control: bool = True,
                  reward_shaper: Optional[RewardShaper] = None, max_num_steps: int = 500, load_coef: float = 0.1,
                  start_iter: int = 0, auto_reset: bool = True, multi_agent: bool = False, env_id_offset: int = 0,
-                 wind_time_series: Optional[np.ndarray] = None, exact_host_trig: Optional[bool] = None):
+                 wind_time_series: Optional[np.ndarray] = None, exact_host_trig: Optional[bool] = None,
+                 turbulence_intensity_range: Optional[tuple] = None):
         case = get_layout(layout) if isinstance(layout, str) else layout
         self.farm_case = case
         self.num_envs = int(num_envs)
@@ -90,6 +91,10 @@ class VecWindFarmEnv:
             assert series.ndim == 2 and series.shape[1] >= 2, "time series rows are [speed, direction]"
             self._series = torch.as_tensor(series[:, :2], device=self.device)
             self._series_pos = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
+        # extension (BASELINE.json configs[2]): ambient TI sampled per env at reset, U(lo, hi); the reference fixes 0.06
+        self.turbulence_intensity_range = turbulence_intensity_range
+        self._ti = torch.full((self.num_envs,), float(self.backend.cfg.turbulence_intensity), dtype=torch.float64,
+                              device=self.device)
         self._zeros_bool = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.episode_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
@@ -135,6 +140,12 @@ class VecWindFarmEnv:
             self._series_pos[torch.as_tensor(ids, device=self.device)] = torch.as_tensor(start, device=self.device)
             first = self._series[self._series_pos[torch.as_tensor(ids, device=self.device)]].cpu().numpy()
             ws, wd = first[:, 0], first[:, 1]
+        if self.turbulence_intensity_range is not None:
+            lo_ti, hi_ti = self.turbulence_intensity_range
+            ti = np.array([np.random.default_rng(None if seed is None else (seed + self.env_id_offset + int(b), 1))
+                           .uniform(lo_ti, hi_ti) for b in ids])
+            self._ti[torch.as_tensor(ids, device=self.device)] = torch.as_tensor(ti, device=self.device)
+            self.backend.set_turbulence_intensity(self._ti)
         out = self.backend.reset(ws, wd, env_ids=ids.astype(np.int32), host_trig=self.exact_host_trig,
                                  warmup_solves=self.start_iter + 1)
         self._iters[ids] = self.start_iter + 1
@@ -175,6 +186,12 @@ class VecWindFarmEnv:
                 truncated = truncated.clone()
                 reward = reward.clone()
                 ws, wd = self.sample_wind_device()
+                if self.turbulence_intensity_range is not None:
+                    lo_ti, hi_ti = self.turbulence_intensity_range
+                    fresh = lo_ti + (hi_ti - lo_ti) * torch.rand(self.num_envs, dtype=torch.float64, device=self.device,
+                                                                 generator=self._gen)
+                    self._ti = torch.where(truncated, fresh, self._ti)
+                    self.backend.set_turbulence_intensity(self._ti)
                 out = self.backend.reset_masked(mask.clone(), ws, wd, warmup_solves=self.start_iter + 1)
                 obs = self._obs(out)
                 self.episode_returns[truncated] = 0
