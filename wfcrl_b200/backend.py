@@ -161,6 +161,24 @@ class FlorisBatch:
         self.last_h2d_bytes, self.last_d2h_bytes = up.value, down.value
         return {k: self._host[k] for k in fields}
 
+    def update_command_host(self, yaw_host: Optional[np.ndarray] = None):
+        """FlorisInterface.update_command from HOST memory in one library call (wf_update_command_host): float64 [B, T]
+        yaw command in (or None), measures out as numpy views of pinned buffers (overwritten by the next call)."""
+        if self._host is None:
+            self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.out.items()}
+        if getattr(self, "_host_np", None) is None:
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
+            names = ("yaw", "wind_speed", "wind_direction", "power", "load", "reward", "freewind", "truncated")
+            self._host_struct = _lib.WfStepOut(*[(self._host[k].data_ptr() if k != "reward" else None) for k in names])
+            self._yaw_pin = torch.empty(self.B, self.T, dtype=torch.float64).pin_memory()
+            self._yaw_pin_np = self._yaw_pin.numpy()
+        ptr = None
+        if yaw_host is not None:
+            self._yaw_pin_np[...] = yaw_host
+            ptr = C.c_void_p(self._yaw_pin.data_ptr())
+        _lib.check(self.lib.wf_update_command_host(self.handle, ptr, C.byref(self._host_struct)))
+        return self._host_np
+
     def set_turbulence_intensity(self, ti: torch.Tensor):
         assert ti.dtype == torch.float64 and ti.is_cuda and ti.shape == (self.B,)
         _lib.check(self.lib.wf_set_turbulence_intensity(self.handle, _ptr(ti), self._stream()))

@@ -3,7 +3,8 @@ de-facto protocol ``WindFarmMDP`` uses).
 
 ``FlorisInterface`` here has the reference class's name, constructor arguments, attributes and method contracts
 (wfcrl/interface.py:444-671) but no FLORIS inside: every ``update_command`` is one launch of the sm_100a step kernel in
-FP64 interface mode through the C-ABI (``wf_update_command``), as a batch of one environment.  The batched environments
+FP64 interface mode (warp-per-env kernel by default, ``kernel="basic"`` selects the one-thread-per-turbine kernel)
+through the C-ABI (``wf_update_command``), as a batch of one environment.  The batched environments
 (``wfcrl_b200.vector_env``) use the same kernels in env mode without this per-call host round trip.
 """
 from __future__ import annotations
@@ -59,7 +60,7 @@ class FlorisInterface(BaseInterface):
     def __init__(self, num_turbines: int, simul_file=None, max_iter: int = int(1e4), log_file: str = None,
                  wind_speed: float = None, wind_direction: float = None,
                  wind_time_series: Union[str, np.ndarray] = None, *, xcoords=None, ycoords=None, device: int = 0,
-                 precision: str = "f64"):
+                 precision: str = "f64", kernel: str = "fast"):
         """``simul_file`` (the FLORIS yaml of the reference) may be a dict with ``xcoords``/``ycoords`` or None when the
         coordinates are passed by keyword; the flow/wake parameters are the template's (case.yaml), baked into the
         library's default config."""
@@ -75,7 +76,7 @@ class FlorisInterface(BaseInterface):
         assert len(xcoords) == num_turbines == len(ycoords)
         self.num_turbines = num_turbines
         self._torch = torch
-        self.fi = FlorisBatch(xcoords, ycoords, 1, device=device, precision=precision, kernel="basic",
+        self.fi = FlorisBatch(xcoords, ycoords, 1, device=device, precision=precision, kernel=kernel,
                               max_iter=int(max_iter))
         self.measure_map = self.DEFAULT_MEASURE_MAP
         self._num_measures = 7
@@ -162,18 +163,15 @@ class FlorisInterface(BaseInterface):
 
     # -- the hot call ---------------------------------------------------------------------------------------------
     def update_command(self, yaw: np.ndarray = None):
-        torch = self._torch
         if yaw is not None:
             self._current_yaw_command[0, 0, :] = np.asarray(yaw).astype(np.double)
         self.update_wind(*next(self.wind_generator))
-        cmd = torch.as_tensor(self._current_yaw_command.reshape(1, -1), device=self.fi.device)
-        out = self.fi.update_command(cmd.contiguous())
-        torch.cuda.current_stream(self.fi.device).synchronize()
+        out = self.fi.update_command_host(self._current_yaw_command.reshape(1, -1))  # one library call, host buffers
         self.current_measures[:, self.measure_map["yaw"]] = self._current_yaw_command[0, 0]
-        self.current_measures[:, self.measure_map["wind_speed"]] = out["wind_speed"][0].cpu().numpy()
-        self.current_measures[:, self.measure_map["wind_direction"]] = out["wind_direction"][0].cpu().numpy()
-        self.current_measures[:, self.measure_map["load"]] = out["load"][0].cpu().numpy()  # already x1e7
-        self._powers = out["power"][0].double().cpu().numpy()  # W in interface mode
+        self.current_measures[:, self.measure_map["wind_speed"]] = out["wind_speed"][0]
+        self.current_measures[:, self.measure_map["wind_direction"]] = out["wind_direction"][0]
+        self.current_measures[:, self.measure_map["load"]] = out["load"][0]  # already x1e7
+        self._powers = out["power"][0].astype(np.float64)  # W in interface mode
         self._num_iter += 1
         if self._logging:
             with open(self._log_file, "a") as fp:
