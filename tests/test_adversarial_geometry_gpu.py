@@ -61,9 +61,6 @@ def test_planted_mask_boundaries(cuda_device, seed, precision, kernel, tol):
 
 def test_geometry_index_table_matches_fp64_masks(cuda_device):
     """The fast kernels' per-source mask indices equal a direct FP64 evaluation of the four masks."""
-    import ctypes as C
-
-    from wfcrl_b200 import _lib
     from wfcrl_b200.backend import FlorisBatch
 
     rng = np.random.default_rng(7)

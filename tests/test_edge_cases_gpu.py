@@ -96,8 +96,10 @@ def test_invalid_arguments(cuda_device):
     fb = FlorisBatch(lx, ly, 2)
     with pytest.raises(_lib.WfError):
         fb.reset([8.0], [270.0], env_ids=[5])
-    with pytest.raises(AssertionError):
+    with pytest.raises(ValueError):
         fb.step(torch.zeros(2, 4, device="cuda"))
+    with pytest.raises(TypeError):
+        fb.step(torch.zeros(2, 3, device="cuda", dtype=torch.float64))
     with pytest.raises(KeyError):
         fb.get_state("nope")
     fb.close()

@@ -127,7 +127,8 @@ class FlorisBatch:
     def reset_masked(self, mask: torch.Tensor, wind_speed: torch.Tensor, wind_direction: torch.Tensor,
                      warmup_solves: int = 1):
         """Device-side reset of the envs where ``mask`` (uint8 [B]) is non-zero; no host round trip."""
-        assert mask.dtype == torch.uint8 and wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64
+        if not (mask.dtype == torch.uint8 and wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64):
+            raise TypeError("mask must be uint8, wind_speed / wind_direction float64 (CUDA tensors of shape [B])")
         _lib.check(self.lib.wf_reset_masked(self.handle, _ptr(mask), _ptr(wind_speed), _ptr(wind_direction),
                                             int(warmup_solves), C.byref(self._out_struct), self._stream()))
         return self.out
@@ -135,22 +136,30 @@ class FlorisBatch:
     def step(self, action: torch.Tensor):
         """One env step for every env; ``action`` float32 [B, T] on the device.  Returns the output tensor dict
         (overwritten in place every call)."""
-        assert action.dtype == torch.float32 and action.is_cuda and action.is_contiguous()
-        assert action.shape == (self.B, self.T)
+        if not (torch.is_tensor(action) and action.dtype == torch.float32 and action.is_cuda and action.is_contiguous()):
+            raise TypeError("action must be a contiguous float32 CUDA tensor")
+        if tuple(action.shape) != (self.B, self.T):
+            raise ValueError(f"action must have shape ({self.B}, {self.T}), got {tuple(action.shape)}")
         _lib.check(self.lib.wf_step(self.handle, _ptr(action), C.byref(self._out_struct), self._stream()))
         return self.out
 
     def update_command(self, yaw: Optional[torch.Tensor] = None):
         """FlorisInterface.update_command(yaw) for every env (interface.py:557-586); power in W, loads x1e7."""
         if yaw is not None:
-            assert yaw.dtype == torch.float64 and yaw.is_cuda and yaw.is_contiguous() and yaw.shape == (self.B, self.T)
+            if not (yaw.dtype == torch.float64 and yaw.is_cuda and yaw.is_contiguous()):
+                raise TypeError("yaw must be a contiguous float64 CUDA tensor")
+            if tuple(yaw.shape) != (self.B, self.T):
+                raise ValueError(f"yaw must have shape ({self.B}, {self.T}), got {tuple(yaw.shape)}")
         _lib.check(self.lib.wf_update_command(self.handle, _ptr(yaw), C.byref(self._out_struct), self._stream()))
         return self.out
 
     def step_host(self, action_host: torch.Tensor, fields=("yaw", "wind_speed", "wind_direction", "reward",
                                                            "truncated", "power", "load", "freewind")):
         """End-to-end step from HOST memory (pinned recommended): H2D action, step, D2H of ``fields``, sync."""
-        assert action_host.dtype == torch.float32 and not action_host.is_cuda and action_host.is_contiguous()
+        if not (action_host.dtype == torch.float32 and not action_host.is_cuda and action_host.is_contiguous()):
+            raise TypeError("action_host must be a contiguous float32 HOST tensor (pinned recommended)")
+        if tuple(action_host.shape) != (self.B, self.T):
+            raise ValueError(f"action_host must have shape ({self.B}, {self.T})")
         if self._host is None:
             self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.out.items()}
         names = ("yaw", "wind_speed", "wind_direction", "power", "load", "reward", "freewind", "truncated")
@@ -180,14 +189,16 @@ class FlorisBatch:
         return self._host_np
 
     def set_turbulence_intensity(self, ti: torch.Tensor):
-        assert ti.dtype == torch.float64 and ti.is_cuda and ti.shape == (self.B,)
+        if not (ti.dtype == torch.float64 and ti.is_cuda and tuple(ti.shape) == (self.B,)):
+            raise TypeError("ti must be a float64 CUDA tensor of shape [B]")
         _lib.check(self.lib.wf_set_turbulence_intensity(self.handle, _ptr(ti), self._stream()))
 
     def update_wind(self, wind_speed: torch.Tensor, wind_direction: torch.Tensor, mask: Optional[torch.Tensor] = None,
                     host_trig: bool = False):
         """FlorisInterface.update_wind for every (or the masked) env: new free-stream wind, counters untouched.
         ``host_trig=True`` computes cosd/sind of the deviation with numpy (one host round trip) for bit-exact geometry."""
-        assert wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64
+        if not (wind_speed.dtype == torch.float64 and wind_direction.dtype == torch.float64):
+            raise TypeError("wind_speed / wind_direction must be float64 CUDA tensors of shape [B]")
         cs = None
         if host_trig:
             wd = wind_direction.detach().cpu().numpy()

@@ -468,11 +468,17 @@ cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst6
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                   const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
     const size_t smem = fast64_smem_bytes(m.T);
-    cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     wf_step_fast64_kernel<<<env_count, 32, smem, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
