@@ -20,6 +20,8 @@
 #include "wf_device.cuh"
 #include "wf_fast_baked.inc"
 
+#include <stdlib.h>
+
 namespace {
 
 // model constant `name`: a compile-time literal in the specialised (BAKED) instantiation, a kernel parameter otherwise
@@ -530,7 +532,8 @@ static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& 
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    wf_step_fast_kernel<BAKED><<<env_count, 32, smem, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    static const size_t pad = getenv("WFCRL_SMEM_PAD") ? (size_t)atoi(getenv("WFCRL_SMEM_PAD")) : 0;  // tuning experiments
+    wf_step_fast_kernel<BAKED><<<env_count, 32, smem + pad, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 

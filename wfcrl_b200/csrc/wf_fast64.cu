@@ -224,6 +224,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
         const double kyd = fc.ka * tpre + fc.kb;
         const double delta0 = tan_th * x0d;
         const double Kck = Kc / kyd;
+        const double inv_x0d = 1.0 / x0d;
 
         // own transverse velocities + yaw-added recovery (in-place TI update)
         const uchar4 ix = sm.idx[i];
@@ -252,6 +253,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
         // A.8 velocity-model scalars with the updated TI
         const double x0v = D * cy * (1.0 + sq1ct) / (1.4142135623730951 * (fc.alpha4 * tpost + beta_term));
         const double kyv = fc.ka * tpost + fc.kb;
+        const double inv_x0v = 1.0 / x0v;
         const double sz0v = fc.near_c * (0.5 / 0.501);
         const double sy0v = sz0v * cy;
         const double near_s = fc.near_c * sqrt(ct);
@@ -285,19 +287,24 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
             const double q = yL * yL;
             const double E = exp(-q * fc.inv_eps2);
             double Vk[3], Wk[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {  // not unrolled: keeps the FP64 kernel inside the instruction cache
                 // pairs (real a, ground mirror b): (0,2) top, (1,3) bottom, (4,5) wake rotation
                 const double r0 = q + fc.zz2[0][k], r2 = q + fc.zz2[2][k], r1 = q + fc.zz2[1][k], r3 = q + fc.zz2[3][k];
                 const double r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
-                const double g0 = Gt / (r0 * r2), g1 = Gb / (r1 * r3), g4 = Gwr / (r4 * r5);
+                // ONE division for the three pair denominators and the downstream decay (products stay < 1e60)
+                const double p02 = r0 * r2, p13 = r1 * r3, p45 = r4 * r5, dd = fc.nu4[k] * dx + eps2;
+                const double P = p02 * p13, Q = p45 * dd;
+                const double inv = 1.0 / (P * Q);
+                const double iP = inv * Q, iQ = inv * P;
+                const double g0 = Gt * (iP * p13), g1 = Gb * (iP * p02), g4 = Gwr * (iQ * dd);
+                const double dec = c_dec * (iQ * p45);
                 const double Xa0 = (1.0 - E * fc.ez[0][k]) * r2, Xb0 = (1.0 - E * fc.ez[2][k]) * r0;
                 const double Xa1 = (1.0 - E * fc.ez[1][k]) * r3, Xb1 = (1.0 - E * fc.ez[3][k]) * r1;
                 const double Xa4 = (1.0 - E * fc.ez[4][k]) * r5, Xb4 = (1.0 - E * fc.ez[5][k]) * r4;
                 const double SV = g0 * (fc.zz[0][k] * Xa0 - fc.zz[2][k] * Xb0) + g1 * (fc.zz[1][k] * Xa1 - fc.zz[3][k] * Xb1) +
                                   g4 * (fc.zz[4][k] * Xa4 - fc.zz[5][k] * Xb4);
                 const double SW = g0 * (Xa0 - Xb0) + g1 * (Xa1 - Xb1) + g4 * (Xa4 - Xb4);
-                const double dec = c_dec / (fc.nu4[k] * dx + eps2);
                 Vk[k] = SV * dec;
                 Wk[k] = fmax(SW * (-yL * dec), 0.0);
             }
@@ -322,7 +329,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
             const double lin = fc.bd * dx + fc.ad;
             double defl;
             if (dx <= x0d) {
-                defl = dx / x0d * delta0 + lin;
+                defl = dx * inv_x0d * delta0 + lin;
             } else {
                 const double dd = dx - x0d;
                 const double sgy = kyd * dd + sy0d, sgz = kyd * dd + sz0d;
@@ -334,13 +341,15 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
             {
                 const bool far = dx >= x0v;
                 const double dd = dx - x0v;
-                const double up = dx / x0v, down = (x0v - dx) / x0v;
+                const double up = dx * inv_x0v, down = (x0v - dx) * inv_x0v;
                 const double sgy = far ? kyv * dd + sy0v : down * near_s + up * sy0v;
                 const double sgz = far ? kyv * dd + sz0v : down * near_s + up * sz0v;
-                const double dy = (dyc - defl) / sgy;
-                const double dcl = dclamp(1.0 - ctc / (sgy * sgz), 0.0, 1.0);
+                const double inv = 1.0 / (sgy * sgz);  // one division: 1/sgy = sgz*inv, 1/sgz = sgy*inv
+                const double dy = (dyc - defl) * (sgz * inv);
+                const double rz = sgy * inv;
+                const double dcl = dclamp(1.0 - ctc * inv, 0.0, 1.0);
                 base = (1.0 - sqrt(dcl)) * exp(-0.5 * dy * dy);
-                ek = exp(-0.5 * fc.dz2[0] / (sgz * sgz));
+                ek = exp(-0.5 * fc.dz2[0] * rz * rz);
             }
             const double be = base * ek;
             const double dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
