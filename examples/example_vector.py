@@ -21,6 +21,8 @@ lo, hi = shard_range(total_envs, rank, world)
 env = envs.make_vec("HornsRev1_Floris", hi - lo, device=local, precision="f32", max_num_steps=500, env_id_offset=lo)
 obs = env.reset(seed=0)
 policy_gain = -0.05  # toy proportional policy: steer every turbine back towards zero yaw, plus exploration noise
+for k in range(10):  # warm-up (lazy CUDA / RNG initialisation)
+    obs, *_ = env.step(policy_gain * obs["yaw"] + torch.randn_like(obs["yaw"]))
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for k in range(steps):
