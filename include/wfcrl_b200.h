@@ -171,6 +171,7 @@ int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);
 /*
  * State access for tests / checkpoint-resume (synchronous).  `name` is one of
  *   "yaw" f64[B][T] | "acc" f32[B][T] | "acc_prev" f32[B][T] | "num_iter" i32[B] | "num_moves" i32[B] |
+ *   "nonfinite" i32[B] (guard counter: env steps whose reward was NaN/Inf since creation) |
  *   "ws" f64[B] | "wd" f64[B] | "ws_norm" f64[B] | "shaper_ref" f64[B] | "ti_ambient" f64[B] |
  *   "order" i32[B][T] | "xs" f64[B][T] | "ys" f64[B][T] | "xi" f64[B][T] | "yi" f64[B][T] | "cs" f64[B][2]
  * `bytes` must equal the full array size.

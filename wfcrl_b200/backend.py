@@ -20,7 +20,7 @@ _SHAPER = {"none": _lib.SHAPER_NONE, "reference": _lib.SHAPER_REFERENCE_PCT, "st
 
 _STATE_DTYPES = {
     "yaw": (np.float64, "BT"), "acc": (np.float32, "BT"), "acc_prev": (np.float32, "BT"),
-    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
+    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "nonfinite": (np.int32, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
     "ws_norm": (np.float64, "B"), "shaper_ref": (np.float64, "B"), "ti_ambient": (np.float64, "B"),
     "order": (np.int32, "BT"), "xs": (np.float64, "BT"), "ys": (np.float64, "BT"), "xi": (np.float64, "BT"),
     "yi": (np.float64, "BT"), "cs": (np.float64, "B2"),
@@ -224,6 +224,27 @@ class FlorisBatch:
         dt, kind = _STATE_DTYPES[name]
         arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), self._shape(kind)))
         _lib.check(self.lib.wf_set_state(self.handle, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    # checkpoint / resume: the complete env state is a handful of small arrays
+    _CHECKPOINT = ("yaw", "acc", "acc_prev", "num_iter", "num_moves", "nonfinite", "ws", "wd", "ws_norm", "shaper_ref",
+                   "ti_ambient")
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        """Host copy of everything needed to resume the batch exactly where it is (geometry is rebuilt from wd)."""
+        sd = {name: self.get_state(name) for name in self._CHECKPOINT}
+        sd["cs"] = self.get_state("cs")
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, np.ndarray]) -> None:
+        """Restore a ``state_dict``: wind first (rebuilds the rotated/sorted geometry with the saved cos/sin so the
+        geometry is bit-identical), then counters, yaw and accumulators."""
+        ws = torch.as_tensor(np.ascontiguousarray(sd["ws"]), device=self.device)
+        wd = torch.as_tensor(np.ascontiguousarray(sd["wd"]), device=self.device)
+        cs = torch.as_tensor(np.ascontiguousarray(sd["cs"]), device=self.device)
+        _lib.check(self.lib.wf_update_wind(self.handle, None, _ptr(ws), _ptr(wd), _ptr(cs), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        for name in self._CHECKPOINT:
+            self.set_state(name, sd[name])
 
     def device_info(self) -> Dict[str, int]:
         vals = [C.c_int32() for _ in range(6)]

@@ -166,6 +166,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     const size_t BT = (size_t)B * T;
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -379,7 +380,7 @@ static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
     const WfState& s = h->st;
     struct { const char* n; void* p; size_t b; } tab[] = {
         {"yaw", s.yaw, BT * 8}, {"acc", s.acc, BT * 4}, {"acc_prev", s.acc_prev, BT * 4},
-        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
+        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
         {"ws_norm", s.ws_norm, B * 8}, {"shaper_ref", s.shaper_ref, B * 8}, {"ti_ambient", s.ti_amb, B * 8},
         {"order", s.order, BT * 4}, {"xs", s.xs, BT * 8}, {"ys", s.ys, BT * 8}, {"xi", s.xi, BT * 8},
         {"yi", s.yi, BT * 8}, {"cs", s.cs, B * 16}};

@@ -32,6 +32,7 @@ struct WfState {
     float* acc_prev;    // [B][T] accumulator one joint action earlier (multi-agent staleness)
     int* num_iter;      // [B] FlorisInterface._num_iter
     int* num_moves;     // [B] WindFarmEnv.num_moves
+    int* nonfinite;     // [B] number of env steps whose reward came out NaN/Inf (guard counter)
     double* ws;         // [B] free-stream wind speed
     double* wd;         // [B] free-stream wind direction (already % 360)
     double* ws_norm;    // [B] free-stream speed of the PREVIOUS state (reward normalisation, simple_env.py:79)

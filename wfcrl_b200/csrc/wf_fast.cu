@@ -508,6 +508,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
                 s.shaper_ref[b] = (double)reward;
                 reward = shaped;
             }
+            if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((float*)out.reward)[b] = reward;
             s.ws_norm[b] = ws_d;
         }

@@ -465,6 +465,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
                 s.shaper_ref[b] = reward;
                 reward = shaped;
             }
+            if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((double*)out.reward)[b] = reward;
             s.ws_norm[b] = ws;
         }

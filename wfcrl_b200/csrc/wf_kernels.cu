@@ -670,6 +670,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 s.shaper_ref[b] = reward;
                 reward = shaped;
             }
+            if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((R*)out.reward)[b] = (R)reward;
             s.ws_norm[b] = ec.ws;  // next state's freewind measurement (mdp.py:280)
         }
