@@ -22,6 +22,30 @@ from .environments.data_cases import FarmCase
 from .interface import BaseInterface
 
 
+def _action_space(controls: dict, num_turbines: int, continuous: bool):
+    """Per-control action space: a symmetric Box of half-width ``step`` (continuous) or {down, hold, up} per turbine."""
+    if continuous:
+        return spaces.Dict({name: spaces.Box(-spec[2], spec[2], shape=(num_turbines,))
+                            for name, spec in controls.items()})
+    return spaces.Dict({name: spaces.MultiDiscrete([3] * num_turbines) for name in controls})
+
+
+def _state_space(attributes, controls: dict, num_turbines: int, default_bounds: dict):
+    """Box per state attribute with float32 bounds: the control's own range, the default range of a measurement, or the
+    (speed, direction) pair for the farm-level free-stream measurement."""
+    unit = np.ones(num_turbines, dtype=np.float32)
+    boxes = OrderedDict()
+    for attr in attributes:
+        if attr == "freewind_measurements":
+            low = np.array([default_bounds["wind_speed"][0], default_bounds["wind_direction"][0]], dtype=np.float32)
+            high = np.array([default_bounds["wind_speed"][1], default_bounds["wind_direction"][1]], dtype=np.float32)
+        else:
+            lo, hi = (controls[attr][0], controls[attr][1]) if attr in controls else default_bounds[attr]
+            low, high = unit * lo, unit * hi
+        boxes[attr] = spaces.Box(low, high, shape=low.shape)
+    return spaces.Dict(boxes)
+
+
 def clip_to_dict_space(element: dict, space) -> dict:
     """Clip every entry of ``element`` to the bounds of the Box stored under the same key."""
     for key in element:
@@ -63,30 +87,13 @@ class WindFarmMDP:
                          if name not in controls and name in self.interface.measure_map]
         self.state_attributes = list(controls.keys()) + self.measures
 
-        T = self.num_turbines
-        if continuous_control:
-            self.action_space = spaces.Dict({
-                name: spaces.Box(-spec[2], spec[2], shape=(T,)) for name, spec in controls.items()})
-        else:  # 0 / 1 / 2 = down / hold / up
-            self.action_space = spaces.Dict({
-                name: spaces.MultiDiscrete([3 for _ in range(T)]) for name in controls})
-
-        ones = np.ones(T, dtype=np.float32)
-        ws_lo, ws_hi = self.DEFAULT_BOUNDS["wind_speed"]
-        wd_lo, wd_hi = self.DEFAULT_BOUNDS["wind_direction"]
-        boxes = OrderedDict()
-        for attr in self.state_attributes:
-            if attr == "freewind_measurements":
-                low = np.array([ws_lo, wd_lo], dtype=np.float32)
-                high = np.array([ws_hi, wd_hi], dtype=np.float32)
-            elif attr in controls:
-                low, high = ones * controls[attr][0], ones * controls[attr][1]
-            else:
-                low, high = ones * self.DEFAULT_BOUNDS[attr][0], ones * self.DEFAULT_BOUNDS[attr][1]
-            boxes[attr] = spaces.Box(low, high, shape=low.shape)
-        self.state_space = spaces.Dict(boxes)
+        self.action_space = _action_space(controls, self.num_turbines, continuous_control)
+        self.state_space = _state_space(self.state_attributes, controls, self.num_turbines, self.DEFAULT_BOUNDS)
         self.start_state = None
-        self._actuation_accumulator = {name: np.zeros(T, dtype=np.float32) for name in controls}
+        self._actuation_accumulator = self._zero_travel()
+
+    def _zero_travel(self):
+        return {name: np.zeros(self.num_turbines, dtype=np.float32) for name in self.controls}
 
     # -- queries --------------------------------------------------------------------------------------------------
     def get_state_powers(self):
@@ -144,7 +151,7 @@ class WindFarmMDP:
             self.interface.update_command()
         start = OrderedDict((attr, self.interface.get_measure(attr)) for attr in self.state_attributes)
         self.start_state = clip_to_dict_space(start, self.state_space)
-        self._actuation_accumulator = {name: np.zeros(self.num_turbines, dtype=np.float32) for name in self.controls}
+        self._actuation_accumulator = self._zero_travel()
         return self.start_state
 
     def get_controlled_state_transition(self, state: Dict, joint_action: Dict):

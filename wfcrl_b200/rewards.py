@@ -1,59 +1,70 @@
-"""Reward shapers with the call protocol of the reference (wfcrl/rewards.py:4-46): ``shaper(reward)`` and ``reset()``.
+"""Reward shapers.
 
-In the batched path the same three shapers are fused into the kernel epilogue (``WfConfig.reward_shaper``); these
-host-side classes serve the single-env drop-in path and carry the ``kernel_code`` the batched path needs."""
+Drop-in for the reference's ``wfcrl.rewards`` (wfcrl/rewards.py:4-46): a shaper is called with the raw cooperative reward
+of a step and returns the shaped one; ``reset()`` is invoked by the env at episode start.  The three shapers exist twice in
+this package: here (host side, single-env path) and fused into the step kernels' epilogue for the batched path -- the
+``kernel_code`` attribute is the link between the two (``FlorisBatch(reward_shaper=kernel_code)``).
+"""
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
 
 
 class RewardShaper(ABC):
-    kernel_code = None  # name understood by FlorisBatch(reward_shaper=...); None = host-only shaper
+    """Base class: subclasses implement ``shape``; instances are callables."""
+
+    #: name of the fused implementation in the step kernel, ``None`` for host-only shapers
+    kernel_code = None
+
+    def __call__(self, reward):
+        return self.shape(reward)
 
     @abstractmethod
-    def __call__(self, reward: float):
-        ...
+    def shape(self, reward):
+        raise NotImplementedError
 
     def update(self):
-        pass
+        """Hook kept for API compatibility (unused)."""
 
     def reset(self):
-        pass
+        """Called at every ``env.reset``; stateless shapers ignore it."""
 
 
 class DoNothingReward(RewardShaper):
-    """Identity."""
+    """Pass the reward through unchanged."""
 
     kernel_code = "none"
 
-    def __call__(self, reward):
+    def shape(self, reward):
         return reward
 
 
 class ReferencePercentage(RewardShaper):
-    """Relative improvement over a fixed reference."""
+    """Relative gain with respect to a constant ``reference`` reward."""
 
     kernel_code = "reference"
 
     def __init__(self, reference: float):
         self.reference = reference
 
-    def __call__(self, reward):
-        return (reward - self.reference) / self.reference
+    def shape(self, reward):
+        gain = reward - self.reference
+        return gain / self.reference
 
 
 class StepPercentage(RewardShaper):
-    """Relative improvement over the previous step's reward; 0 while the reference is 0."""
+    """Relative gain with respect to the previous step's raw reward (0 until a non-zero reference exists)."""
 
     kernel_code = "step"
 
     def __init__(self, reference: float = 0.0):
         self.reference = reference
 
-    def __call__(self, reward):
-        shaped = 0.0 if self.reference == 0 else (reward - self.reference) / self.reference
-        self.reference = reward
-        return shaped
+    def shape(self, reward):
+        previous, self.reference = self.reference, reward
+        if previous == 0:
+            return 0.0
+        return (reward - previous) / previous
 
     def reset(self, reference: float = 0.0):
         self.reference = reference
