@@ -92,3 +92,19 @@ def test_zero_yaw_symmetry_and_wake_loss():
     sol = floris_oracle.solve([0.0, 630.0, 1260.0], [0.0, 0.0, 0.0], 8.0, 270.0, np.zeros(3))
     assert sol.power_W[0] > sol.power_W[2] > 0 and sol.power_W[0] > sol.power_W[1] > 0
     assert np.all(sol.ti >= 0.06 - 1e-15)
+
+
+def test_wake_steering_pays_off_on_an_aligned_row():
+    """Physical plausibility of the yawed (parity-unpinned) branch: steering the wakes of an aligned row away from the
+    downstream rotors raises the farm's total power, and the gain is roughly symmetric in the yaw sign (the asymmetry comes
+    from the wake-rotation vortex of GCH)."""
+    lx, ly = [0.0, 630.0, 1260.0], [0.0, 0.0, 0.0]
+    base = floris_oracle.solve(lx, ly, 8.0, 270.0, [0.0, 0.0, 0.0]).power_W.sum()
+    pos = floris_oracle.solve(lx, ly, 8.0, 270.0, [20.0, 10.0, 0.0]).power_W.sum()
+    neg = floris_oracle.solve(lx, ly, 8.0, 270.0, [-20.0, -10.0, 0.0]).power_W.sum()
+    assert pos > 1.10 * base and neg > 1.10 * base
+    assert abs(pos - neg) / base < 0.05 and pos != neg
+    # the yawed turbine itself loses power roughly like cos(yaw)^pP
+    p0 = floris_oracle.solve(lx, ly, 8.0, 270.0, [0.0, 0.0, 0.0]).power_W[0]
+    p20 = floris_oracle.solve(lx, ly, 8.0, 270.0, [20.0, 0.0, 0.0]).power_W[0]
+    assert abs(p20 / p0 - np.cos(np.radians(20.0)) ** 1.88) < 0.01
