@@ -257,7 +257,7 @@ int wf_oracle_solve(int T, const double* lx, const double* ly, double ws, double
         }
 
         /* A.6 deflection needs TI_i BEFORE the yaw-added-recovery update; A.8 needs it AFTER */
-        double x0d[NP], kyd[NP], delta0[NP], thc0[NP], farK[NP], sM0[NP], sy0d[NP], sz0d[NP];
+        double x0d[NP], kyd[NP], delta0[NP], farK[NP], sM0[NP], sy0d[NP], sz0d[NP];
         for (int p = 0; p < NP; ++p) {
             const double U = U0[p % G];
             double uR = U * ct * cg / (2.0 * (1 - sqrt(1 - (ct * cg))));
@@ -270,7 +270,6 @@ int wf_oracle_solve(int T, const double* lx, const double* ly, double ws, double
             sy0d[p] = sz0d[p] * cg * cosd(0.0);
             double th = DM * (0.3 * radians(g) / cg);
             th = th * (1 - sqrt(1 - ct * cg));
-            thc0[p] = th;
             delta0[p] = tan(th) * (x0d[p] - x_i);
             sM0[p] = sqrt(M0);
             farK[p] = th * E0 / 5.2 * sqrt(sy0d[p] * sz0d[p] / (kyd[p] * kyd[p] * M0));
