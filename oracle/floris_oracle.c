@@ -227,8 +227,6 @@ int wf_oracle_solve(int T, const double* lx, const double* ly, double ws, double
         double* Vw = defc; /* reuse scratch: store V in defc, W in a second scratch */
         double* Ww = (double*)malloc(sizeof(double) * (size_t)T * NP);
         for (int t = 0; t < T; ++t) {
-            double Xt[NP];
-            for (int p = 0; p < NP; ++p) Xt[p] = xs[t];
             const double dx = xs[t] - x_i;
             for (int p = 0; p < NP; ++p) {
                 const int k = p % G;
