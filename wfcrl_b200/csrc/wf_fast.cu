@@ -1,19 +1,28 @@
 // Tuned FP32 step kernel for sm_100a: ONE WARP PER ENVIRONMENT (CTA = 32 threads = one env / wind condition).
 //
-// Design (DESIGN.md "fast kernel"):
-//  * the whole per-env solver state lives in shared memory: for every rotor grid point the running sum of squared
-//    velocity deficits (SOSFS), v and w; per turbine the running maximum of the wake-added turbulence, the rotated
-//    coordinates as float-float pairs and the precomputed FP64 mask indices.  ~12.9 KB per env at T = 80, so 16 envs
-//    are resident per SM and no block-level barrier exists anywhere (only __syncwarp).
-//  * sequential solver over sources i; for each source every lane first computes the (warp-uniform) source
-//    prologue redundantly -- no cross-lane traffic -- then the warp sweeps the downstream targets in passes of
-//    10 turbines x 3 lateral grid columns (30 of 32 lanes busy); each lane handles the 3 vertical points of its
-//    column, so deflection, wake widths and the lateral Gaussian are evaluated once per column.
-//  * x-direction masks are NOT evaluated in floating point here: the geometry kernel (FP64) stores, per source,
-//    the first target index at which each mask turns true, so the kernel is FP64-free.
-//  * algebra legal in FP32 mode only: exp(-(y^2+z^2)/eps^2) = exp(-y^2/eps^2) * const_z, paired reciprocals,
-//    uR/(U0+u0) = 1/2, self-induced vortex velocities and the secondary-steering integrals as per-model constants,
-//    sum of squares instead of a hypot chain.
+// Design:
+//  * the whole per-env solver state lives in shared memory: per rotor grid point the running sum of squared velocity
+//    deficits (SOSFS) and the pair (v, w); per (turbine, lateral column) the running maximum of the wake-added
+//    turbulence; the rotated coordinates as float-float pairs; the precomputed FP64 mask indices; a queue of target
+//    ids.  13.1 KB per env at T = 80 -> 16 envs resident per SM; no block-level barrier anywhere (only __syncwarp).
+//  * sequential solver over sources i.  Per source:
+//      1. prologue: rotor sums by a butterfly over the 9 lanes that own the source's grid points, then the warp-uniform
+//         scalar chain (Ct, induction, secondary steering, deflection / velocity-model scalars, yaw-added recovery)
+//         evaluated redundantly by every lane -- no broadcast needed;
+//      2. V sweep over ALL downstream targets, 10 turbines x 3 lateral grid columns per pass (30 of 32 lanes), each lane
+//         doing the 3 vertical points of its column: the three vortex pairs (real + ground mirror) and the (v, w)
+//         update; the same pass ballots a compacted queue of the targets that can see the velocity deficit;
+//      3. D sweep over the queue only: deflection, wake widths, Gaussian deficit, sum-of-squares update, overlap count
+//         and wake-added turbulence.
+//  * x-direction masks are NOT evaluated in floating point here: the geometry kernel (FP64) stores, per source, the
+//    first target index at which each mask turns true, so the kernel is FP64-free.
+//  * algebra legal in FP32 mode only (each changes results by <= ~1e-6 relative): exp(-(y^2+z^2)/eps^2) =
+//    exp(-y^2/eps^2) * const_z; one reciprocal per vortex pair; uR/(U0+u0) = 1/2; mirror-vortex cores = 1;
+//    self-induced vortex velocities and the secondary-steering integrals as per-model constants; sum of squares instead
+//    of a hypot chain; deficit contributions below exp(-5.5^2/2) dropped.
+//  * BAKED instantiation: the per-model constants are compile-time literals generated at build time (wf_fast_baked.inc)
+//    and used as instruction immediates; the generic instantiation reads them from kernel parameters / a shared-memory
+//    float4 block.
 //
 // Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
 // wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
