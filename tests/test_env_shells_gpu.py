@@ -228,3 +228,35 @@ def test_make_vec_sampled_turbulence_intensity(cuda_device):
         ref = c_oracle.solve(lx, ly, fw[b, 0], fw[b, 1], np.zeros(16), ti_ambient=ti[b])
         assert np.allclose(obs["wind_speed"][b].cpu().numpy(), np.clip(ref.ws_local, 3, 28), rtol=1e-9)
     env.close()
+
+
+def test_single_env_wind_time_series_matches_oracle(cuda_device):
+    """Wind time-series mode through the drop-in path (interface.py:503-524, 563): random start offset from numpy's global
+    RNG, wind updated before every solve, requested reset winds ignored with a warning."""
+    from wfcrl_b200 import environments as envs
+
+    series = np.array([[8.0, 270.0], [9.5, 262.0], [7.2, 281.0], [11.0, 255.0], [6.4, 275.5]])
+    lx, ly = layout("Turb3_Row1_")
+    np.random.seed(11)
+    env = envs.make("Turb3_Row1_Floris", max_num_steps=12, wind_time_series=series, log=False)
+    np.random.seed(11)
+    ref = env_oracle.EnvOracle(lx, ly, solver=c_oracle.solve, max_num_steps=12, wind_time_series=series)
+    np.random.seed(12)  # the start offset of every reset comes from numpy's GLOBAL generator (interface.py:517)
+    obs = env.reset(seed=0)
+    np.random.seed(12)
+    robs = ref.reset(seed=0)
+    assert np.allclose(obs["freewind_measurements"], robs["freewind_measurements"])
+    rng = np.random.default_rng(1)
+    for _ in range(7):  # runs past the end of the 5-row series? no: 5 rows, start offset + 7 draws would exhaust it
+        a = rng.uniform(-5, 5, 3).astype(np.float32)
+        try:
+            r_out = ref.step({"yaw": a.copy()})
+        except (StopIteration, RuntimeError):
+            with pytest.raises((StopIteration, RuntimeError)):
+                env.step({"yaw": a.copy()})
+            break
+        o, r, _t, tr, info = env.step({"yaw": a.copy()})
+        ro, rr, _rt, rtr, rinfo = r_out
+        assert np.allclose(o["freewind_measurements"], ro["freewind_measurements"])
+        assert abs(r[0] - rr[0]) <= 1e-9 * abs(rr[0]) and tr == rtr
+        assert np.allclose(info["power"], rinfo["power"], rtol=1e-9)

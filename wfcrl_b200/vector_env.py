@@ -162,7 +162,8 @@ class VecWindFarmEnv:
         if not torch.is_tensor(action):
             action = torch.as_tensor(np.asarray(action, dtype=np.float32), device=self.device)
         action = action.to(device=self.device, dtype=torch.float32).contiguous()
-        if self._series is not None:  # time-series mode: the wind moves before every solve (interface.py:563)
+        if self._series is not None:  # time-series mode: the wind moves before every solve (interface.py:563).
+            # Extension: the series is cyclic here; the reference's generator stops after one pass over the rows.
             self._series_pos = (self._series_pos + 1) % self._series.shape[0]
             row = self._series[self._series_pos]
             self.backend.update_wind(row[:, 0].contiguous(), row[:, 1].contiguous(), host_trig=self.exact_host_trig)
