@@ -1,0 +1,53 @@
+"""Large randomized parity sweep of the tuned kernels against the C oracle (evidence for DESIGN.md section 3):
+error distribution of per-turbine power / reward and the rate of discrete flips (overlap-count threshold) in FP32."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from oracle import c_oracle
+from wfcrl_b200.backend import FlorisBatch
+from wfcrl_b200.layouts import layout_xy
+
+out = {}
+for name, B in (("HornsRev1_", 32768), ("Turb32_Row5_", 32768), ("Ablaincourt_", 65536)):
+    lx, ly = layout_xy(name)
+    T = len(lx)
+    rng = np.random.default_rng(2024)
+    ws = np.clip(8 * rng.weibull(8, B), 3, 28)
+    wd = np.clip(rng.normal(270, 20, B) % 360, 0, 360)
+    yaw = rng.uniform(-40, 40, (B, T)).astype(np.float32).astype(np.float64)
+    dev = ((wd - 270.0) % 360.0 + 360.0) % 360.0
+    cs = np.stack([np.cos(np.radians(dev)), np.sin(np.radians(dev))], 1)
+    t0 = time.time()
+    ref = c_oracle.solve_batch(lx, ly, ws, wd, yaw, cs=cs)
+    t_ref = time.time() - t0
+    for precision in ("f32", "f64"):
+        fb = FlorisBatch(lx, ly, B, precision=precision, kernel="fast", max_iter=10)
+        fb.reset(ws, wd, host_trig=True, warmup_solves=0)
+        o = fb.update_command(torch.as_tensor(yaw, device="cuda"))
+        torch.cuda.synchronize()
+        p = o["power"].double().cpu().numpy()
+        err = np.abs(p - ref["power_W"]) / np.maximum(ref["power_W"], 1.0)
+        wsl = o["wind_speed"].double().cpu().numpy()
+        err_ws = np.abs(wsl - ref["ws_local"]) / ref["ws_local"]
+        wdl = o["wind_direction"].double().cpu().numpy()
+        ti = o["load"].double().cpu().numpy()[..., 0] / 1e7
+        ti_jump = np.abs(ti - ref["ti"]) > 1e-3   # a flip of the overlap count moves TI by ~1/9 * 0.03..0.3
+        rec = {
+            "turbines": T, "envs": B, "power_rel_err": {"median": float(np.median(err)), "p99": float(np.percentile(err, 99)),
+                                                       "p99.99": float(np.percentile(err, 99.99)), "max": float(err.max())},
+            "frac_power_err_gt_1e-4": float(np.mean(err > 1e-4)), "frac_power_err_gt_1e-9": float(np.mean(err > 1e-9)),
+            "wind_speed_rel_err_max": float(err_ws.max()), "wind_direction_abs_err_max_deg": float(np.abs(wdl - ref["wd_local"]).max()),
+            "ti_flip_fraction": float(np.mean(ti_jump)), "order_exact": bool(np.array_equal(fb.get_state("order"), ref["order"])),
+            "oracle_seconds": t_ref,
+        }
+        out[f"{name}{precision}"] = rec
+        print(name, precision, rec, flush=True)
+        fb.close()
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/parity_sweep.json", "w"), indent=1)
