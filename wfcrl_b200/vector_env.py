@@ -34,7 +34,7 @@ class VecWindFarmEnv:
                  kernel: Optional[str] = None, controls: Optional[dict] = None, continuous_control: bool = True,
                  reward_shaper: Optional[RewardShaper] = None, max_num_steps: int = 500, load_coef: float = 0.1,
                  start_iter: int = 0, auto_reset: bool = True, multi_agent: bool = False, env_id_offset: int = 0,
-                 wind_time_series: Optional[np.ndarray] = None, exact_host_trig: Optional[bool] = None,
+                 wind_time_series: Optional[Union[str, np.ndarray]] = None, exact_host_trig: Optional[bool] = None,
                  turbulence_intensity_range: Optional[tuple] = None):
         case = get_layout(layout) if isinstance(layout, str) else layout
         self.farm_case = case
@@ -87,6 +87,10 @@ class VecWindFarmEnv:
         self._iters = np.zeros(self.num_envs, dtype=np.int64)  # host mirror of FlorisInterface._num_iter
         self._series = None
         if wind_time_series is not None:
+            if isinstance(wind_time_series, str):  # csv path: first column speed, second direction (interface.py:473-474, 514)
+                import pandas as pd
+
+                wind_time_series = pd.read_csv(wind_time_series).values
             series = np.asarray(wind_time_series, dtype=np.float64)
             assert series.ndim == 2 and series.shape[1] >= 2, "time series rows are [speed, direction]"
             self._series = torch.as_tensor(series[:, :2], device=self.device)
