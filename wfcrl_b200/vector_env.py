@@ -136,7 +136,12 @@ class VecWindFarmEnv:
         per-env arrays) exactly like the reference; otherwise both are sampled per env."""
         ids = np.arange(self.num_envs) if env_ids is None else np.asarray(env_ids)
         options = options or {}
-        ws_s, wd_s = self.sample_wind_host(seed, ids)
+        if seed is None and not ("wind_speed" in options and "wind_direction" in options):
+            # unseeded reset: nothing to reproduce, draw the whole batch on the device in one go
+            ws_d, wd_d = self.sample_wind_device()
+            ws_s, wd_s = ws_d.cpu().numpy()[ids], wd_d.cpu().numpy()[ids]
+        else:
+            ws_s, wd_s = self.sample_wind_host(seed, ids)
         ws = np.broadcast_to(np.asarray(options.get("wind_speed", ws_s), dtype=np.float64), ids.shape)
         wd = np.broadcast_to(np.asarray(options.get("wind_direction", wd_s), dtype=np.float64), ids.shape)
         if self._series is not None:
