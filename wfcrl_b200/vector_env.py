@@ -104,6 +104,7 @@ class VecWindFarmEnv:
         self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         self.finished_returns, self.finished_lengths = [], []
         self._needs_reset = True
+        self.sample_wind_device()  # warm the device RNG now so the first in-loop auto-reset does not pay its lazy init
 
     # -- wind sampling ------------------------------------------------------------------------------------------
     def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray):
