@@ -14,6 +14,7 @@
  *    reference arithmetic) and float with WF_PREC_F32 (fast mode, <=1e-4 relative).
  *  - all `d_*` pointers are DEVICE pointers on the handle's device, all `h_*` pointers are HOST pointers.
  *  - per-turbine arrays are row-major [num_envs][num_turbines] in the ORIGINAL turbine order of the layout.
+ *  - output buffers must be aligned to 16 bytes (`load` is written with 128-bit stores, `freewind` with 64-bit stores).
  *  - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*; NULL = default
  *    stream); no host synchronisation happens inside unless stated.
  *  - there is NO CPU fallback: without a CUDA device `wf_create` fails with WF_ERR_CUDA.
