@@ -23,7 +23,9 @@ def _run(name, B, precision, kernel, seed):
     rng = np.random.default_rng(seed + 1)
     yaw = rng.uniform(-40, 40, (B, T)).astype(np.float32).astype(np.float64)
     yaw[1] = 0.0
-    fb = FlorisBatch(lx, ly, B, precision=precision, kernel=kernel, max_iter=10)
+    yaw[2, ::2] = 0.0   # mixed: the kernel's unyawed-source branch next to yawed sources
+    yaw[3, 1:] = 0.0    # one yawed turbine (the reference notebook's pattern)
+    fb =FlorisBatch(lx, ly, B, precision=precision, kernel=kernel, max_iter=10)
     fb.reset(ws, wd, host_trig=True, warmup_solves=0)
     out = fb.update_command(torch.as_tensor(yaw, device="cuda"))
     torch.cuda.synchronize()
