@@ -271,8 +271,6 @@ def run_ours(args):
         rng = np.random.default_rng(gid0 + b)
         ws[b] = np.clip(8 * rng.weibull(8), 3, 28)
         wd[b] = np.clip(rng.normal(270, 20) % 360, 0, 360)
-    d_ws, d_wd = torch.as_tensor(ws, device=dev), torch.as_tensor(wd, device=dev)
-    all_mask = torch.ones(B, dtype=torch.uint8, device=dev)
 
     # synthetic yaw-action stream U(-5, 5), a pool of distinct device buffers cycled through
     gen = torch.Generator(device=dev)
@@ -289,7 +287,7 @@ def run_ours(args):
         out = fb.step(pool[k % len(pool)])
         steps_in_episode += 1
         if steps_in_episode >= MAX_NUM_STEPS - 1:  # every env truncates together: device-side reset, new episode
-            fb.reset_masked(all_mask, d_ws, d_wd)
+            fb.reset_sampled(None, seed=0, env_id_offset=gid0)  # fresh winds, keyed by (global env id, episode)
             steps_in_episode = 0
         return out
 

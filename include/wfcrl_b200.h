@@ -130,6 +130,18 @@ int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const
                     int32_t warmup_solves, const WfStepOut* out, void* stream);
 
 /*
+ * wf_reset_masked with the winds drawn inside the library from the reference's reset distribution (mdp.py:242-258:
+ * ws = clip(8 * Weibull(8), 3, 28), wd = clip(N(270, 20) % 360, 0, 360)).  numpy's Generator stream cannot be reproduced
+ * on the device, so the draws come from Philox4x32-10 with key = seed and counter = (env_id_offset + b, episode index
+ * of env b): an env's winds depend on its GLOBAL id and on how many sampled resets it has had ("episode" state array),
+ * never on how the envs are sharded over handles / GPUs.  ws by Weibull inversion, wd by Box-Muller.  When
+ * ti_hi > ti_lo the ambient turbulence intensity of the selected envs is drawn U(ti_lo, ti_hi) as well (extension; the
+ * reference fixes 0.06, case.yaml:33); pass ti_lo = ti_hi = 0 to leave it alone.  d_mask NULL = all envs.  Asynchronous.
+ */
+int wf_reset_sampled(WfHandle h, const uint8_t* d_mask, uint64_t seed, int64_t env_id_offset, double ti_lo, double ti_hi,
+                     int32_t warmup_solves, const WfStepOut* out, void* stream);
+
+/*
  * ENV MODE.  Replaces one WindFarmEnv.step / one full MAWindFarmEnv agent cycle for every env:
  * actuation-rate constraint (simple_env.py:65-72), action clip + yaw transition in float32 + accumulator
  * (mdp.py:291-319), FlorisInterface.update_command (interface.py:557-586), powers/1e6 and loads/1e7
@@ -173,6 +185,7 @@ int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);
  * State access for tests / checkpoint-resume (synchronous).  `name` is one of
  *   "yaw" f64[B][T] | "acc" f32[B][T] | "acc_prev" f32[B][T] | "num_iter" i32[B] | "num_moves" i32[B] |
  *   "nonfinite" i32[B] (guard counter: env steps whose reward was NaN/Inf since creation) |
+ *   "episode" i32[B] (sampled resets so far: the counter word of wf_reset_sampled) |
  *   "ws" f64[B] | "wd" f64[B] | "ws_norm" f64[B] | "shaper_ref" f64[B] | "ti_ambient" f64[B] |
  *   "order" i32[B][T] | "xs" f64[B][T] | "ys" f64[B][T] | "xi" f64[B][T] | "yi" f64[B][T] | "cs" f64[B][2]
  * `bytes` must equal the full array size.

@@ -394,3 +394,38 @@ class MAEnvOracle:
         self.agent_selection = self._sel.next()
         for a, r in self.rewards.items():  # _accumulate_rewards
             self._cumulative_rewards[a] += r
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Checker of the library's device-side reset sampler (wf_reset_sampled).  NOT a reference algorithm: the reference draws
+# from numpy's Generator (mdp.py:235-258), whose stream cannot be reproduced on a GPU; the library draws the same
+# DISTRIBUTION from Philox4x32-10 keyed by (seed; global env id, episode index).  This restatement pins the words and
+# the transforms so the tests can check the draws value by value and against the reference's distribution.
+# ----------------------------------------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al. 2011): counter = 4 words, key = 2 words -> 4 words."""
+    c = [int(x) & 0xFFFFFFFF for x in counter]
+    k = [int(x) & 0xFFFFFFFF for x in key]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def _u53(a, b):
+    return (((a >> 5) << 26) | (b >> 6)) / 9007199254740992.0
+
+
+def sampled_reset_wind(seed: int, global_env_id: int, episode: int, ti_range=None):
+    """(wind_speed, wind_direction[, ti]) the library draws for this (seed, env, episode)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    g = (global_env_id & 0xFFFFFFFF, (global_env_id >> 32) & 0xFFFFFFFF)
+    r0 = philox4x32_10((g[0], g[1], episode, 0), key)
+    r1 = philox4x32_10((g[0], g[1], episode, 1), key)
+    ws = float(np.clip(8.0 * (-np.log1p(-_u53(r0[0], r0[1]))) ** 0.125, 3.0, 28.0))
+    z = np.sqrt(-2.0 * np.log1p(-_u53(r0[2], r0[3]))) * np.cos(2.0 * np.pi * _u53(r1[0], r1[1]))
+    wd = float(np.clip((270.0 + 20.0 * z) % 360.0, 0.0, 360.0))
+    if ti_range is None:
+        return ws, wd
+    return ws, wd, ti_range[0] + (ti_range[1] - ti_range[0]) * _u53(r1[2], r1[3])

@@ -120,3 +120,25 @@ def test_multiagent_truncation_and_agent_iter_terminates():
             n_live += 1
     assert n_live == 3 * 4  # max_num_steps=5 -> 4 cycles before truncation
     assert env.agents == []
+
+
+def test_philox_known_answers_and_reset_distribution():
+    """Checker of the library's reset sampler: Philox4x32-10 against the Random123 known-answer vectors, and the sampled
+    (wind speed, wind direction) against the reference's reset distribution (mdp.py:242-258) drawn with numpy."""
+    from scipy import stats
+
+    assert env_oracle.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert env_oracle.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert env_oracle.philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    n = 3000
+    draws = np.array([env_oracle.sampled_reset_wind(11, g, e) for g in range(n // 2) for e in range(2)])
+    rng = np.random.default_rng(5)
+    ref_ws = np.clip(8 * rng.weibull(8, 20000), 3, 28)
+    ref_wd = np.clip(rng.normal(270, 20, 20000) % 360, 0, 360)
+    assert stats.ks_2samp(draws[:, 0], ref_ws).pvalue > 1e-3
+    assert stats.ks_2samp(draws[:, 1], ref_wd).pvalue > 1e-3
+    assert abs(np.corrcoef(draws[:, 0], draws[:, 1])[0, 1]) < 0.06       # independent draws
+    assert abs(np.corrcoef(draws[0::2, 0], draws[1::2, 0])[0, 1]) < 0.08  # consecutive episodes of an env
+    ws, wd, ti = env_oracle.sampled_reset_wind(11, 3, 0, ti_range=(0.04, 0.12))
+    assert (ws, wd) == tuple(draws[6]) and 0.04 <= ti < 0.12

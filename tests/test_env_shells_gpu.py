@@ -260,3 +260,86 @@ def test_single_env_wind_time_series_matches_oracle(cuda_device):
         assert np.allclose(o["freewind_measurements"], ro["freewind_measurements"])
         assert abs(r[0] - rr[0]) <= 1e-9 * abs(rr[0]) and tr == rtr
         assert np.allclose(info["power"], rinfo["power"], rtol=1e-9)
+
+
+def test_reset_sampled_draws_match_checker_and_ignore_sharding(cuda_device):
+    """wf_reset_sampled: the library's counter-based reset sampler reproduces the checker value by
+    value, advances the per-env episode counter only for the selected envs, and depends on global env ids only."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb6_Row2_")
+    B, seed = 12, 0x1234_5678_9ABC
+    fb = FlorisBatch(lx, ly, B, precision="f64", kernel="fast", max_iter=10)
+    out = fb.reset_sampled(None, seed, env_id_offset=0)
+    fw = out["freewind"].cpu().numpy().copy()
+    want = np.array([env_oracle.sampled_reset_wind(seed, g, 0) for g in range(B)])
+    assert np.allclose(fw, want, rtol=1e-13, atol=0)
+    assert np.array_equal(fb.get_state("ws"), fw[:, 0]) and list(fb.get_state("episode")) == [1] * B
+    sol = c_oracle.solve(lx, ly, fw[3, 0], fw[3, 1], np.zeros(6))
+    assert np.allclose(out["wind_speed"][3].cpu().numpy(), sol.ws_local, rtol=1e-9)   # warm-up solve ran on the new wind
+    assert list(fb.get_state("num_iter")) == [1] * B
+    # masked second episode with TI: only the selected envs move on
+    mask = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    mask[[2, 5]] = 1
+    out = fb.reset_sampled(mask, seed, 0, turbulence_intensity_range=(0.04, 0.12))
+    fw2 = out["freewind"].cpu().numpy()
+    ti = fb.get_state("ti_ambient")
+    for g in range(B):
+        if g in (2, 5):
+            ws, wd, t = env_oracle.sampled_reset_wind(seed, g, 1, ti_range=(0.04, 0.12))
+            assert np.allclose(fw2[g], [ws, wd], rtol=1e-13) and abs(ti[g] - t) < 1e-15
+        else:
+            assert np.array_equal(fw2[g], fw[g]) and ti[g] == 0.06
+    assert list(fb.get_state("episode")) == [2 if g in (2, 5) else 1 for g in range(B)]
+    fb.close()
+    # two shards with global offsets draw the same bits as the single batch
+    for lo, hi in ((0, 5), (5, 12)):
+        sh = FlorisBatch(lx, ly, hi - lo, precision="f64", kernel="fast", max_iter=10)
+        o = sh.reset_sampled(None, seed, env_id_offset=lo)
+        assert np.array_equal(o["freewind"].cpu().numpy(), fw[lo:hi])
+        sh.close()
+    # argument validation through the C-ABI
+    fb = FlorisBatch(lx, ly, 2, precision="f32", kernel="fast", max_iter=10)
+    with pytest.raises(Exception, match="env_id_offset"):
+        fb.reset_sampled(None, 1, env_id_offset=-1)
+    fb.close()
+
+
+def test_vec_env_autoreset_trajectories_ignore_sharding(cuda_device):
+    """Two episodes with in-loop auto-resets: a 2-shard run reproduces the single-batch run bit for bit (wind of the
+    second episode included), for seeded and for unseeded-but-same-key starts."""
+    import torch
+
+    from wfcrl_b200 import environments as envs
+
+    B, T, max_steps = 8, 6, 4
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    acts = [torch.rand(B, T, device="cuda", generator=gen) * 10 - 5 for _ in range(7)]
+
+    def run(envs_and_ranges, seed):
+        rows = []
+        for e, _lo, _hi in envs_and_ranges:
+            if seed is None:
+                e._seed = 99
+            e.reset(seed=seed)
+        for a in acts:
+            parts = [e.step(a[lo:hi].contiguous()) for e, lo, hi in envs_and_ranges]
+            rows.append((torch.cat([p[0]["freewind_measurements"] for p in parts]).clone(),
+                         torch.cat([p[1] for p in parts]).clone(), torch.cat([p[3] for p in parts]).clone()))
+        return rows
+
+    for seed in (21, None):
+        full = [(envs.make_vec("Turb6_Row2_Floris", B, precision="f32", max_num_steps=max_steps), 0, B)]
+        halves = [(envs.make_vec("Turb6_Row2_Floris", 4, precision="f32", max_num_steps=max_steps, env_id_offset=lo), lo, lo + 4)
+                  for lo in (0, 4)]
+        ra, rb = run(full, seed), run(halves, seed)
+        n_trunc = 0
+        for (fa, wa, ta), (fb_, wb, tb) in zip(ra, rb):
+            assert torch.equal(fa, fb_) and torch.equal(wa, wb) and torch.equal(ta, tb)
+            n_trunc += int(ta.all())
+        assert n_trunc == 2
+        assert not torch.equal(ra[0][0], ra[-1][0])   # the wind did change across episodes
+        for e, *_ in full + halves:
+            e.close()

@@ -20,7 +20,7 @@ _SHAPER = {"none": _lib.SHAPER_NONE, "reference": _lib.SHAPER_REFERENCE_PCT, "st
 
 _STATE_DTYPES = {
     "yaw": (np.float64, "BT"), "acc": (np.float32, "BT"), "acc_prev": (np.float32, "BT"),
-    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "nonfinite": (np.int32, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
+    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "nonfinite": (np.int32, "B"), "episode": (np.int32, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
     "ws_norm": (np.float64, "B"), "shaper_ref": (np.float64, "B"), "ti_ambient": (np.float64, "B"),
     "order": (np.int32, "BT"), "xs": (np.float64, "BT"), "ys": (np.float64, "BT"), "xi": (np.float64, "BT"),
     "yi": (np.float64, "BT"), "cs": (np.float64, "B2"),
@@ -122,6 +122,19 @@ class FlorisBatch:
         _lib.check(self.lib.wf_reset(self.handle, vp(ids), n, vp(ws), vp(wd), vp(hc), vp(hs), int(warmup_solves),
                                      C.byref(self._out_struct), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # host staging arrays above must outlive the copies
+        return self.out
+
+    def reset_sampled(self, mask: Optional[torch.Tensor], seed: int, env_id_offset: int = 0, warmup_solves: int = 1,
+                      turbulence_intensity_range: Optional[tuple] = None):
+        """Device-side reset with the winds drawn inside the library from the reference's reset distribution
+        (wfcrl/mdp.py:242-258) by a counter-based generator keyed by (seed, env_id_offset + env, episode index): the
+        draws do not depend on how the envs are sharded over handles / GPUs.  ``mask`` uint8 [B] or None (= all)."""
+        if mask is not None and mask.dtype != torch.uint8:
+            raise TypeError("mask must be a uint8 CUDA tensor of shape [B]")
+        lo, hi = turbulence_intensity_range if turbulence_intensity_range is not None else (0.0, 0.0)
+        _lib.check(self.lib.wf_reset_sampled(self.handle, _ptr(mask) if mask is not None else None,
+                                             int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset), float(lo), float(hi),
+                                             int(warmup_solves), C.byref(self._out_struct), self._stream()))
         return self.out
 
     def reset_masked(self, mask: torch.Tensor, wind_speed: torch.Tensor, wind_direction: torch.Tensor,
@@ -226,7 +239,7 @@ class FlorisBatch:
         _lib.check(self.lib.wf_set_state(self.handle, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
     # checkpoint / resume: the complete env state is a handful of small arrays
-    _CHECKPOINT = ("yaw", "acc", "acc_prev", "num_iter", "num_moves", "nonfinite", "ws", "wd", "ws_norm", "shaper_ref",
+    _CHECKPOINT = ("yaw", "acc", "acc_prev", "num_iter", "num_moves", "nonfinite", "episode", "ws", "wd", "ws_norm", "shaper_ref",
                    "ti_ambient")
 
     def state_dict(self) -> Dict[str, np.ndarray]:

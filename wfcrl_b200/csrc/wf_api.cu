@@ -166,7 +166,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     const size_t BT = (size_t)B * T;
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
-        (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -238,6 +238,18 @@ int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const
     h->launches += 2;
     for (int k = 0; k < warmup; ++k) TRY(launch_step(h, WF_MODE_WARMUP, d_mask, nullptr, nullptr, to_ptrs(out), st));
     return WF_OK;
+}
+
+int wf_reset_sampled(WfHandle h, const uint8_t* d_mask, uint64_t seed, int64_t env_id_offset, double ti_lo, double ti_hi,
+                     int32_t warmup, const WfStepOut* out, void* stream) {
+    if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
+    if (env_id_offset < 0) return set_err(WF_ERR_INVALID, "env_id_offset must be >= 0");
+    if (ti_hi > ti_lo && !(ti_lo > 0.0)) return set_err(WF_ERR_INVALID, "turbulence-intensity range must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(wf_launch_sample_reset(h->model, h->st, d_mask, seed, env_id_offset, ti_lo, ti_hi, h->d_rws, h->d_rwd, st));
+    h->launches += 1;
+    return wf_reset_masked(h, d_mask, h->d_rws, h->d_rwd, warmup, out, stream);
 }
 
 int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const double* wd, const double* hc,
@@ -380,7 +392,7 @@ static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
     const WfState& s = h->st;
     struct { const char* n; void* p; size_t b; } tab[] = {
         {"yaw", s.yaw, BT * 8}, {"acc", s.acc, BT * 4}, {"acc_prev", s.acc_prev, BT * 4},
-        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
+        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"episode", s.episode, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
         {"ws_norm", s.ws_norm, B * 8}, {"shaper_ref", s.shaper_ref, B * 8}, {"ti_ambient", s.ti_amb, B * 8},
         {"order", s.order, BT * 4}, {"xs", s.xs, BT * 8}, {"ys", s.ys, BT * 8}, {"xi", s.xi, BT * 8},
         {"yi", s.yi, BT * 8}, {"cs", s.cs, B * 16}};

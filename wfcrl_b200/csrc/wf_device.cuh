@@ -33,6 +33,7 @@ struct WfState {
     int* num_iter;      // [B] FlorisInterface._num_iter
     int* num_moves;     // [B] WindFarmEnv.num_moves
     int* nonfinite;     // [B] number of env steps whose reward came out NaN/Inf (guard counter)
+    int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
     double* ws;         // [B] free-stream wind speed
     double* wd;         // [B] free-stream wind direction (already % 360)
     double* ws_norm;    // [B] free-stream speed of the PREVIOUS state (reward normalisation, simple_env.py:79)
@@ -104,6 +105,9 @@ cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, cons
                                  int env_begin, int env_count, cudaStream_t stream);
 cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                const double* d_wd, cudaStream_t stream);
+cudaError_t wf_launch_sample_reset(const WfModel& m, const WfState& s, const uint8_t* d_mask, unsigned long long seed,
+                                   long long env_id_offset, double ti_lo, double ti_hi, double* d_ws, double* d_wd,
+                                   cudaStream_t stream);
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                   const double* d_wd, cudaStream_t stream);
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);

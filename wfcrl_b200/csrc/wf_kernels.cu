@@ -238,6 +238,51 @@ __global__ void wf_set_wind_kernel(const WfModel m, const WfState s, const uint8
     s.wd[b] = fmod_py(wd[b], 360.0);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// reset sampler: the reference's reset distribution (mdp.py:242-258) from a counter-based generator
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  key = the user's 64-bit seed, counter = (global env id lo, hi, episode index
+// of that env, draw index): every (env, episode) owns its words no matter how the envs are sharded over handles or
+// GPUs, so 1/2/4/8-GPU runs reset to identical winds.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// 53-bit uniform in [0, 1) from two words (the construction numpy's Generator.random uses on 64-bit output)
+__device__ __forceinline__ double u53(unsigned a, unsigned b) {
+    return (double)(((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void wf_sample_reset_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
+                                       const unsigned long long seed, const long long env_id_offset, const double ti_lo,
+                                       const double ti_hi, double* __restrict__ ws, double* __restrict__ wd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.B || (mask && !mask[b])) return;
+    const unsigned long long gid = (unsigned long long)(env_id_offset + b);
+    const unsigned ep = (unsigned)s.episode[b];
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    const uint4 r0 = philox4x32_10(make_uint4((unsigned)gid, (unsigned)(gid >> 32), ep, 0u), key);
+    const uint4 r1 = philox4x32_10(make_uint4((unsigned)gid, (unsigned)(gid >> 32), ep, 1u), key);
+    // wind speed = clip(8 * Weibull(k = 8), 3, 28) by inversion (mdp.py:242-247): Weibull(k) = Exp(1)^(1/k)
+    const double e1 = -log1p(-u53(r0.x, r0.y));
+    ws[b] = fmin(fmax(8.0 * pow(e1, 0.125), 3.0), 28.0);
+    // wind direction = clip(N(270, 20) % 360, 0, 360) (mdp.py:253-258), Box-Muller on two uniforms
+    const double rad = sqrt(-2.0 * log1p(-u53(r0.z, r0.w)));
+    const double z = rad * cospi(2.0 * u53(r1.x, r1.y));
+    wd[b] = fmin(fmax(fmod_py(270.0 + 20.0 * z, 360.0), 0.0), 360.0);
+    // extension (BASELINE.json configs[2]): ambient TI ~ U(ti_lo, ti_hi) per episode; the reference fixes it (case.yaml:33)
+    if (ti_hi > ti_lo) s.ti_amb[b] = ti_lo + (ti_hi - ti_lo) * u53(r1.z, r1.w);
+    s.episode[b] = (int)(ep + 1u);
+}
+
 // reset per-env scalars/accumulators for masked envs
 __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
                                       const double* __restrict__ ws, const double* __restrict__ wd) {
@@ -693,6 +738,13 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
 cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                const double* d_wd, cudaStream_t stream) {
     wf_set_wind_kernel<<<(m.B + 127) / 128, 128, 0, stream>>>(m, s, d_mask, d_ws, d_wd);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_sample_reset(const WfModel& m, const WfState& s, const uint8_t* d_mask, unsigned long long seed,
+                                   long long env_id_offset, double ti_lo, double ti_hi, double* d_ws, double* d_wd,
+                                   cudaStream_t stream) {
+    wf_sample_reset_kernel<<<(m.B + 127) / 128, 128, 0, stream>>>(m, s, d_mask, seed, env_id_offset, ti_lo, ti_hi, d_ws, d_wd);
     return cudaGetLastError();
 }
 

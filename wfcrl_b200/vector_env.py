@@ -82,8 +82,9 @@ class VecWindFarmEnv:
         ]))
         self.action_space = self.single_action_space
         self.observation_space = self.single_observation_space
-        self._gen = torch.Generator(device=self.device)
+        self._gen = torch.Generator(device=self.device)  # time-series start offsets of in-loop resets only
         self._gen.manual_seed(0x5EED + self.env_id_offset)
+        self._seed = int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFFFFFF  # replaced by reset(seed=...)
         self._iters = np.zeros(self.num_envs, dtype=np.int64)  # host mirror of FlorisInterface._num_iter
         self._series = None
         if wind_time_series is not None:
@@ -97,14 +98,11 @@ class VecWindFarmEnv:
             self._series_pos = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         # extension (BASELINE.json configs[2]): ambient TI sampled per env at reset, U(lo, hi); the reference fixes 0.06
         self.turbulence_intensity_range = turbulence_intensity_range
-        self._ti = torch.full((self.num_envs,), float(self.backend.cfg.turbulence_intensity), dtype=torch.float64,
-                              device=self.device)
         self._zeros_bool = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.episode_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         self.finished_returns, self.finished_lengths = [], []
         self._needs_reset = True
-        self.sample_wind_device()  # warm the device RNG now so the first in-loop auto-reset does not pay its lazy init
 
     # -- wind sampling ------------------------------------------------------------------------------------------
     def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray):
@@ -118,15 +116,6 @@ class VecWindFarmEnv:
             wd[k] = np.clip(rng.normal(270, 20) % 360, 0, 360)
         return ws, wd
 
-    def sample_wind_device(self):
-        """Same distribution drawn on the device (Philox), used for in-loop auto-resets (no host round trip)."""
-        B = self.num_envs
-        u = torch.rand(B, dtype=torch.float64, device=self.device, generator=self._gen)
-        ws = (8.0 * (-torch.log1p(-u)).pow(1.0 / 8.0)).clamp_(3.0, 28.0)
-        wd = torch.remainder(270.0 + 20.0 * torch.randn(B, dtype=torch.float64, device=self.device,
-                                                        generator=self._gen), 360.0).clamp_(0.0, 360.0)
-        return ws, wd
-
     # -- API ------------------------------------------------------------------------------------------------------
     def _obs(self, out):
         return OrderedDict([("yaw", out["yaw"]), ("freewind_measurements", out["freewind"]),
@@ -134,32 +123,46 @@ class VecWindFarmEnv:
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None, env_ids=None):
         """Reset all (or ``env_ids``) envs.  ``options`` may carry ``wind_speed`` / ``wind_direction`` (scalars or
-        per-env arrays) exactly like the reference; otherwise both are sampled per env."""
+        per-env arrays) exactly like the reference; otherwise both are sampled per env.
+
+        ``seed=s`` draws env ``g``'s wind with numpy exactly as the reference's ``reset(seed=s + g)`` would and makes
+        ``s`` the key of all later in-loop resets; ``seed=None`` draws on the device (``wf_reset_sampled``).  Either way
+        an env's winds depend on its GLOBAL id and episode index only, not on the sharding."""
         ids = np.arange(self.num_envs) if env_ids is None else np.asarray(env_ids)
+        idt = torch.as_tensor(ids, device=self.device)
         options = options or {}
-        if seed is None and not ("wind_speed" in options and "wind_direction" in options):
-            # unseeded reset: nothing to reproduce, draw the whole batch on the device in one go
-            ws_d, wd_d = self.sample_wind_device()
-            ws_s, wd_s = ws_d.cpu().numpy()[ids], wd_d.cpu().numpy()[ids]
-        else:
-            ws_s, wd_s = self.sample_wind_host(seed, ids)
-        ws = np.broadcast_to(np.asarray(options.get("wind_speed", ws_s), dtype=np.float64), ids.shape)
-        wd = np.broadcast_to(np.asarray(options.get("wind_direction", wd_s), dtype=np.float64), ids.shape)
+        warm = self.start_iter + 1
+        if seed is not None:
+            self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            episode = self.backend.get_state("episode")
+            episode[ids] = 0
+            self.backend.set_state("episode", episode)
+        given = "wind_speed" in options and "wind_direction" in options
         if self._series is not None:
             start = np.random.randint(0, self._series.shape[0], size=len(ids))  # interface.py:517
-            self._series_pos[torch.as_tensor(ids, device=self.device)] = torch.as_tensor(start, device=self.device)
-            first = self._series[self._series_pos[torch.as_tensor(ids, device=self.device)]].cpu().numpy()
-            ws, wd = first[:, 0], first[:, 1]
-        if self.turbulence_intensity_range is not None:
-            lo_ti, hi_ti = self.turbulence_intensity_range
-            ti = np.array([np.random.default_rng(None if seed is None else (seed + self.env_id_offset + int(b), 1))
-                           .uniform(lo_ti, hi_ti) for b in ids])
-            self._ti[torch.as_tensor(ids, device=self.device)] = torch.as_tensor(ti, device=self.device)
-            self.backend.set_turbulence_intensity(self._ti)
-        out = self.backend.reset(ws, wd, env_ids=ids.astype(np.int32), host_trig=self.exact_host_trig,
-                                 warmup_solves=self.start_iter + 1)
-        self._iters[ids] = self.start_iter + 1
-        idt = torch.as_tensor(ids, device=self.device)
+            self._series_pos[idt] = torch.as_tensor(start, device=self.device)
+        if seed is None and not given and self._series is None:
+            # nothing to reproduce on the host: winds (and TI) drawn by the library for the selected envs
+            mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            mask[idt] = 1
+            out = self.backend.reset_sampled(mask, self._seed, self.env_id_offset, warm, self.turbulence_intensity_range)
+        else:
+            if self._series is not None:
+                first = self._series[self._series_pos[idt]].cpu().numpy()
+                ws, wd = first[:, 0], first[:, 1]
+            else:
+                ws_s, wd_s = (None, None) if given else self.sample_wind_host(seed, ids)
+                ws = np.broadcast_to(np.asarray(options.get("wind_speed", ws_s), dtype=np.float64), ids.shape)
+                wd = np.broadcast_to(np.asarray(options.get("wind_direction", wd_s), dtype=np.float64), ids.shape)
+            if self.turbulence_intensity_range is not None:
+                lo_ti, hi_ti = self.turbulence_intensity_range
+                ti = self.backend.get_state("ti_ambient")
+                ti[ids] = [np.random.default_rng(None if seed is None else (seed + self.env_id_offset + int(b), 1))
+                           .uniform(lo_ti, hi_ti) for b in ids]
+                self.backend.set_turbulence_intensity(torch.as_tensor(ti, device=self.device))
+            out = self.backend.reset(ws, wd, env_ids=ids.astype(np.int32), host_trig=self.exact_host_trig,
+                                     warmup_solves=warm)
+        self._iters[ids] = warm
         self.episode_returns[idt] = 0
         self.episode_lengths[idt] = 0
         self._needs_reset = False
@@ -196,14 +199,15 @@ class VecWindFarmEnv:
                 info["final_info"] = {"power": out["power"].clone(), "load": out["load"].clone()}
                 truncated = truncated.clone()
                 reward = reward.clone()
-                ws, wd = self.sample_wind_device()
-                if self.turbulence_intensity_range is not None:
-                    lo_ti, hi_ti = self.turbulence_intensity_range
-                    fresh = lo_ti + (hi_ti - lo_ti) * torch.rand(self.num_envs, dtype=torch.float64, device=self.device,
-                                                                 generator=self._gen)
-                    self._ti = torch.where(truncated, fresh, self._ti)
-                    self.backend.set_turbulence_intensity(self._ti)
-                out = self.backend.reset_masked(mask.clone(), ws, wd, warmup_solves=self.start_iter + 1)
+                if self._series is not None:  # the wind generator restarts at a random row (interface.py:517)
+                    start = torch.randint(0, self._series.shape[0], (self.num_envs,), device=self.device, generator=self._gen)
+                    self._series_pos = torch.where(truncated, start, self._series_pos)
+                    row = self._series[self._series_pos]
+                    out = self.backend.reset_masked(mask.clone(), row[:, 0].contiguous(), row[:, 1].contiguous(),
+                                                    warmup_solves=self.start_iter + 1)
+                else:
+                    out = self.backend.reset_sampled(mask.clone(), self._seed, self.env_id_offset, self.start_iter + 1,
+                                                     self.turbulence_intensity_range)
                 obs = self._obs(out)
                 self.episode_returns[truncated] = 0
                 self.episode_lengths[truncated] = 0
