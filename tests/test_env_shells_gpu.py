@@ -343,3 +343,40 @@ def test_vec_env_autoreset_trajectories_ignore_sharding(cuda_device):
         assert not torch.equal(ra[0][0], ra[-1][0])   # the wind did change across episodes
         for e, *_ in full + halves:
             e.close()
+
+
+def test_vec_log_wrapper_ring_buffers(cuda_device):
+    """Device-side history: chronological, wraps around, logs the finished episode's last rows on
+    auto-reset steps; works for the centralised and the decentralised batch."""
+    import torch
+
+    from wfcrl_b200 import environments as envs
+
+    B, T = 4, 6
+    env = envs.make_vec("Turb6_Row2_Floris", B, precision="f64", max_num_steps=4, log=5)
+    plain = envs.make_vec("Turb6_Row2_Floris", B, precision="f64", max_num_steps=4)
+    env.reset(seed=9)
+    plain.reset(seed=9)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    seen = []
+    for k in range(7):
+        a = torch.rand(B, T, device="cuda", generator=gen) * 10 - 5
+        env.step(a)
+        obs, rew, _t, trunc, info = plain.step(a)
+        last = info.get("final_observation", obs)
+        seen.append((last["yaw"].clone(), rew.clone(), info.get("final_info", info)["power"].clone(), trunc.clone()))
+    h = env.history
+    assert h["reward"].shape == (5, B) and h["observation"]["yaw"].shape == (5, B, T) and h["load"].shape == (5, B, T, 4)
+    for row, (yaw, rew, power, trunc) in enumerate(seen[-5:]):
+        assert torch.equal(h["observation"]["yaw"][row], yaw) and torch.equal(h["reward"][row], rew)
+        assert torch.equal(h["power"][row], power) and torch.equal(h["truncated"][row], trunc)
+    assert h["truncated"][:, 0].tolist() == [True, False, False, True, False]   # steps 2..6, truncation at 2 and 5
+    assert float(h["observation"]["yaw"][0].abs().max()) > 0   # the truncation row is the episode's last state, not the restart
+    env.close()
+    plain.close()
+    dec = envs.make_vec("Dec_Turb3_Row1_Floris", 2, precision="f32", max_num_steps=10, log=8)
+    dec.reset(seed=1)
+    for _ in range(3):
+        dec.step(torch.ones(2, 3, device="cuda"))
+    assert dec.history["reward"].shape == (3, 2) and dec.history["observation"]["yaw"][-1, 0].tolist() == [3.0, 3.0, 3.0]
+    dec.close()

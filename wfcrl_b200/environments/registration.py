@@ -66,10 +66,11 @@ def make(env_id: str, controls: Union[dict, list] = ["yaw"], log=True, **env_kwa
     return env
 
 
-def make_vec(env_id: str, num_envs: int, controls: Union[dict, list] = ["yaw"], **env_kwargs):
+def make_vec(env_id: str, num_envs: int, controls: Union[dict, list] = ["yaw"], log: int = 0, **env_kwargs):
     """Batched counterpart of ``make``: ``num_envs`` independent copies of ``env_id`` on one GPU, stepped by one kernel
     launch (``VecWindFarmEnv`` / ``VecMAWindFarmEnv``).  Extra kwargs: device, precision ("f32" fast / "f64" bit-check),
-    auto_reset, env_id_offset (global id of env 0 when the batch is sharded over ranks)."""
+    auto_reset, env_id_offset (global id of env 0 when the batch is sharded over ranks); ``log=N`` wraps the env in a
+    ``VecLogWrapper`` keeping the last N steps in device-side ring buffers."""
     from ..vector_env import VecMAWindFarmEnv, VecWindFarmEnv
 
     decentralized, name, simulator = _parse(env_id)
@@ -80,7 +81,12 @@ def make_vec(env_id: str, num_envs: int, controls: Union[dict, list] = ["yaw"], 
     layout = {"num_turbines": case.num_turbines, "xcoords": case.xcoords, "ycoords": case.ycoords, "dt": case.dt,
               "t_init": case.t_init}
     cls = VecMAWindFarmEnv if decentralized else VecWindFarmEnv
-    return cls(layout, num_envs, controls=controls, start_iter=math.ceil(case.t_init / case.dt), **env_kwargs)
+    env = cls(layout, num_envs, controls=controls, start_iter=math.ceil(case.t_init / case.dt), **env_kwargs)
+    if log:
+        from ..wrappers import VecLogWrapper
+
+        env = VecLogWrapper(env, capacity=int(log))
+    return env
 
 
 def list_envs():

@@ -212,6 +212,7 @@ class VecWindFarmEnv:
                 self.episode_returns[truncated] = 0
                 self.episode_lengths[truncated] = 0
                 self._iters[done_host] = self.start_iter + 1
+        self.last_info = info  # joint (un-split) info of this step, incl. final_observation on auto-reset steps
         return obs, reward, self._zeros_bool, truncated, info
 
     def episode_statistics(self):
