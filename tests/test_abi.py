@@ -84,6 +84,23 @@ def test_invalid_arguments_are_reported_not_thrown():
     assert lib.wf_create(C.byref(cfg), lx.ctypes.data_as(C.c_void_p), lx.ctypes.data_as(C.c_void_p),
                          C.byref(handle)) == 1
     assert b"num_turbines" in lib.wf_last_error()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    cfg.num_turbines = 3
+    bad = np.array([0.0, np.nan, 500.0])
+    assert lib.wf_create(C.byref(cfg), ptr(bad), ptr(np.zeros(3)), C.byref(handle)) == 1
+    assert b"layout" in lib.wf_last_error()
+    cfg.kernel = 7
+    assert lib.wf_create(C.byref(cfg), ptr(np.zeros(3)), ptr(np.zeros(3)), C.byref(handle)) == 1
+    assert b"kernel" in lib.wf_last_error()
+    lib.wf_default_config(C.byref(cfg))
+    cfg.num_turbines, cfg.num_envs = 3, 1
+    cfg.table_ws[5] = cfg.table_ws[4]
+    assert lib.wf_create(C.byref(cfg), ptr(np.zeros(3)), ptr(np.zeros(3)), C.byref(handle)) == 1
+    assert b"strictly increasing" in lib.wf_last_error()
+    lib.wf_default_config(C.byref(cfg))
+    cfg.num_turbines, cfg.num_envs, cfg.hub_height = 3, 1, 50.0
+    assert lib.wf_create(C.byref(cfg), ptr(np.zeros(3)), ptr(np.zeros(3)), C.byref(handle)) == 1
+    assert b"hub_height" in lib.wf_last_error()
 
 
 def test_product_never_imports_the_oracle():

@@ -100,6 +100,17 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if (cfg->wind_veer != 0.0) return set_err(WF_ERR_INVALID, "wind_veer != 0 is not supported (case.yaml:39 uses 0)");
     if (!(cfg->yaw_lo < cfg->yaw_hi)) return set_err(WF_ERR_INVALID, "yaw bounds: need low < high (mdp.py:196)");
     if (cfg->precision != WF_PREC_F64 && cfg->precision != WF_PREC_F32) return set_err(WF_ERR_INVALID, "bad precision");
+    if (cfg->kernel != WF_KERNEL_BASIC && cfg->kernel != WF_KERNEL_FAST) return set_err(WF_ERR_INVALID, "bad kernel");
+    if (!(cfg->rotor_diameter > 0.0) || !(cfg->hub_height > cfg->rotor_diameter / 2) || !(cfg->dt > 0.0) ||
+        !(cfg->actuator_rate > 0.0) || !(cfg->turbulence_intensity > 0.0) || !(cfg->air_density > 0.0))
+        return set_err(WF_ERR_INVALID, "rotor_diameter, dt, actuator_rate, turbulence_intensity, air_density must be "
+                                       "positive and hub_height > rotor_diameter / 2");
+    for (int i = 0; i < cfg->table_len; ++i)
+        if (!isfinite(cfg->table_ws[i]) || !isfinite(cfg->table_cp[i]) || !isfinite(cfg->table_ct[i]) ||
+            (i > 0 && !(cfg->table_ws[i] > cfg->table_ws[i - 1])))
+            return set_err(WF_ERR_INVALID, "turbine table: wind speeds must be finite and strictly increasing");
+    for (int t = 0; t < T; ++t)
+        if (!isfinite(lx[t]) || !isfinite(ly[t])) return set_err(WF_ERR_INVALID, "layout coordinates must be finite");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
