@@ -158,9 +158,16 @@ int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* strea
 int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, void* stream);
 
 /*
- * End-to-end convenience for hosts without device buffers: copies `h_action` (float [B][T]) host->device, runs
- * wf_step, copies every non-NULL member of `h_out` device->host and synchronises the stream.  Uses pinned staging
- * owned by the handle.  h2d/d2h bytes moved are returned through the optional counters.
+ * End-to-end convenience for hosts without device buffers: `h_action` (float [B][T]) in, wf_step, every non-NULL
+ * member of `h_out` out, synchronous.  Two routes, same results bit for bit:
+ *   - staged: cudaMemcpyAsync into device staging owned by the handle, 6 env chunks on 6 streams so the copies of one
+ *     chunk overlap the kernels of the next (any host memory; pinned is faster);
+ *   - zero-copy: when EVERY buffer is page-locked memory the device can address (cudaHostAlloc / cudaHostRegister,
+ *     e.g. a torch pinned tensor) and B*T <= 163840, the buffers are mapped into the step kernel, which reads the
+ *     commands and writes the results over PCIe itself: one launch, no copy engine, ~25 us less latency per call.
+ *     Beyond that size the copy engines win (measured).
+ * WFCRL_B200_HOST_PATH=staged|zero_copy in the environment forces a route.  The bytes that crossed PCIe are returned
+ * through the optional counters.
  */
 int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* h_out, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 

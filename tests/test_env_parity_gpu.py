@@ -142,18 +142,23 @@ def test_host_path_and_masked_reset(cuda_device):
     B, T = 8, len(lx)
     ws, wd = sample_winds(B, seed=1)
     fa = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=6)
-    fbb = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=6)
-    fa.reset(ws, wd, host_trig=False)
-    fbb.reset(ws, wd, host_trig=False)
+    fbb = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=6)   # pinned buffers: zero-copy launch
+    fcc = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=6)   # pageable action: staged copies
+    for f in (fa, fbb, fcc):
+        f.reset(ws, wd, host_trig=False)
     rng = np.random.default_rng(0)
     for k in range(5):
         a = rng.uniform(-5, 5, (B, T)).astype(np.float32)
         dev = fa.step(torch.as_tensor(a, device="cuda"))
         host = fbb.step_host(torch.as_tensor(a).pin_memory())
+        staged = fcc.step_host(torch.as_tensor(a))
         torch.cuda.synchronize()
-        for key in ("yaw", "power", "reward", "truncated", "load", "wind_speed"):
+        for key in ("yaw", "power", "reward", "truncated", "load", "wind_speed", "wind_direction", "freewind"):
             assert torch.equal(dev[key].cpu(), host[key]), key
-    assert fbb.last_h2d_bytes == B * T * 4 and fbb.last_d2h_bytes > 0
+            assert torch.equal(dev[key].cpu(), staged[key]), key
+    d2h = B * T * 4 * 8 + B * (4 + 8 + 1)
+    assert fbb.last_h2d_bytes == B * T * 4 and fbb.last_d2h_bytes == d2h and fcc.last_d2h_bytes == d2h
+    fcc.close()
     assert bool(dev["truncated"].all())  # max_iter=6: reset consumed 1, 5 steps -> truncated
     mask = torch.zeros(B, dtype=torch.uint8, device="cuda")
     mask[::2] = 1
@@ -164,6 +169,35 @@ def test_host_path_and_masked_reset(cuda_device):
     assert np.all(fa.get_state("yaw")[::2] == 0) and np.any(fa.get_state("yaw")[1::2] != 0)
     fa.close()
     fbb.close()
+
+
+def test_host_path_large_batch_zero_copy_equals_staged(cuda_device, monkeypatch):
+    """4096 envs (the staged pipeline splits into chunks): pinned zero-copy == forced staged == device path."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Ablaincourt_")
+    B, T = 4096 + 37, len(lx)
+    ws, wd = sample_winds(B, seed=2)
+    fbs = [FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=100) for _ in range(3)]
+    for f in fbs:
+        f.reset(ws, wd, host_trig=False)
+    gen = torch.Generator().manual_seed(0)
+    for k in range(3):
+        a = (torch.rand(B, T, generator=gen) * 10 - 5).pin_memory()
+        dev = fbs[0].step(a.cuda())
+        monkeypatch.setenv("WFCRL_B200_HOST_PATH", "zero_copy")
+        zero = fbs[1].step_host(a)
+        monkeypatch.setenv("WFCRL_B200_HOST_PATH", "staged")
+        staged = fbs[2].step_host(a)
+        monkeypatch.delenv("WFCRL_B200_HOST_PATH")
+        torch.cuda.synchronize()
+        for key in ("yaw", "power", "reward", "truncated", "load", "wind_speed", "wind_direction", "freewind"):
+            assert torch.equal(dev[key].cpu(), zero[key]) and torch.equal(zero[key], staged[key]), key
+    assert fbs[1].launch_count() + 5 * 3 == fbs[2].launch_count()   # 1 launch per step vs 6 chunk launches
+    for f in fbs:
+        f.close()
 
 
 def test_device_trig_geometry_matches_host_within_ulp(cuda_device):

@@ -45,7 +45,8 @@ struct WfHandle_t {
     float* d_action = nullptr;
     double* d_yaw_cmd = nullptr;
     WfOutPtrs d_out = {};
-    cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
+    static constexpr int kHostStreams = 6;
+    cudaStream_t host_streams[kHostStreams] = {};  // one per chunk of the wf_step_host pipeline
     uint64_t launches = 0;
 };
 
@@ -85,8 +86,8 @@ int wf_destroy(WfHandle h) {
     if (h->h_rws) cudaFreeHost(h->h_rws);
     if (h->h_rwd) cudaFreeHost(h->h_rwd);
     if (h->h_rcs) cudaFreeHost(h->h_rcs);
-    if (h->host_stream) cudaStreamDestroy(h->host_stream);
-    if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
+    for (cudaStream_t st : h->host_streams)
+        if (st) cudaStreamDestroy(st);
     delete h;
     return WF_OK;
 }
@@ -191,9 +192,9 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         cudaMallocHost((void**)&h->h_rwd, sizeof(double) * B) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_rcs, sizeof(double) * 2 * B) != cudaSuccess)
         return fail(set_err(WF_ERR_NOMEM, "cudaMallocHost failed"));
-    if (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking) != cudaSuccess)
-        return fail(set_err(WF_ERR_CUDA, "cudaStreamCreate failed"));
+    for (cudaStream_t& st : h->host_streams)
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(set_err(WF_ERR_CUDA, "cudaStreamCreate failed"));
 
     // initial condition: wind (8, 270) as in FlorisCase.simul_params (data_cases.py:99-100), ambient TI from the config
     {
@@ -306,11 +307,63 @@ int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, voi
     return launch_step(h, WF_MODE_INTERFACE, nullptr, nullptr, d_yaw, to_ptrs(out), (cudaStream_t)stream);
 }
 
+// Device alias of a host pointer when it is page-locked memory the GPU can address (cudaHostAlloc / cudaHostRegister
+// under unified addressing, e.g. a torch pinned tensor); NULL for pageable memory.
+static void* mapped_alias(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+static constexpr size_t kZeroCopyMaxElems = 163840;  // envs x turbines up to which wf_step_host maps the host buffers
+
 // shared implementation of the two host-buffer entry points
 static int step_host_impl(WfHandle h, int mode, const float* h_action, const double* h_yaw, const WfHostOut* ho,
                           uint64_t* h2d, uint64_t* d2h) {
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t B = h->model.B, T = h->model.T, BT = B * T, es = h->es;
+    const uint64_t up = (h_action ? sizeof(float) * BT : 0) + (h_yaw ? sizeof(double) * BT : 0);
+    const uint64_t down = ((ho->yaw ? BT : 0) + (ho->wind_speed ? BT : 0) + (ho->wind_direction ? BT : 0) +
+                           (ho->power ? BT : 0) + (ho->load ? 4 * BT : 0) + (ho->reward ? B : 0) +
+                           (ho->freewind ? 2 * B : 0)) * es + (ho->truncated ? B : 0);
+    if (h2d) *h2d = up;
+    if (d2h) *d2h = down;
+
+    // ---- zero-copy path: every buffer is mapped pinned memory -> ONE launch, no copy engine.  The kernel reads the
+    // commands and writes the results over PCIe itself (coalesced 128-bit / 32-bit stores from the env epilogue), so
+    // result traffic overlaps the solves of the other envs instead of trailing the last one.
+    // Taken for small batches, where the call is launch- and copy-latency bound; big batches go through the copy
+    // engines: the kernel's result stores are scattered in the original turbine order, which PCIe handles poorly.
+    // WFCRL_B200_HOST_PATH=zero_copy|staged overrides the choice.
+    const char* force = getenv("WFCRL_B200_HOST_PATH");
+    const bool want_zero = force ? !strcmp(force, "zero_copy") : BT <= kZeroCopyMaxElems;
+    if (want_zero) {
+        bool all = true;
+        WfOutPtrs z = {};
+        const float* za = nullptr;
+        const double* zy = nullptr;
+#define ALIAS(dst, src)                                   \
+    if (src) {                                            \
+        void* q = mapped_alias(src);                      \
+        all = all && q != nullptr;                        \
+        dst = static_cast<decltype(dst)>(q);              \
+    }
+        ALIAS(za, h_action) ALIAS(zy, h_yaw) ALIAS(z.yaw, ho->yaw) ALIAS(z.wind_speed, ho->wind_speed)
+        ALIAS(z.wind_direction, ho->wind_direction) ALIAS(z.power, ho->power) ALIAS(z.load, ho->load)
+        ALIAS(z.reward, ho->reward) ALIAS(z.freewind, ho->freewind) ALIAS(z.truncated, ho->truncated)
+#undef ALIAS
+        if (all) {
+            TRY(launch_step(h, mode, nullptr, za, zy, z, h->host_streams[0]));
+            CUDA_TRY(cudaStreamSynchronize(h->host_streams[0]));
+            return WF_OK;
+        }
+    }
+
+    // ---- staged path (pageable buffers): chunks of envs, one stream per chunk, so the copies of chunk c overlap the
+    // kernels of the later chunks; only the last chunk's device->host copies are exposed.
     if (!h->d_action) {
         TRY(dev_alloc(h, &h->d_action, BT));
         TRY(dev_alloc(h, &h->d_yaw_cmd, BT));
@@ -324,8 +377,6 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
         TRY(dev_alloc(h, &p, 2 * B * es)); h->d_out.freewind = p;
         TRY(dev_alloc(h, &h->d_out.truncated, B));
     }
-    // Chunked two-stream pipeline: the device->host copies of chunk c overlap the kernel of chunk c+1.
-    uint64_t up = 0, down = 0;
     WfOutPtrs o = {};
     if (ho->yaw) o.yaw = h->d_out.yaw;
     if (ho->wind_speed) o.wind_speed = h->d_out.wind_speed;
@@ -335,35 +386,26 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
     if (ho->reward) o.reward = h->d_out.reward;
     if (ho->freewind) o.freewind = h->d_out.freewind;
     if (ho->truncated) o.truncated = h->d_out.truncated;
-    const int nchunk = (B >= 2048) ? 4 : 1;
-    cudaStream_t streams[2] = {h->host_stream, h->host_stream2};
+    const int nchunk = (B >= 2048) ? WfHandle_t::kHostStreams : 1;
     for (int c = 0; c < nchunk; ++c) {
         const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
-        cudaStream_t st = streams[c & 1];
-        if (h_action) {
+        cudaStream_t st = h->host_streams[c];
+        if (h_action)
             CUDA_TRY(cudaMemcpyAsync(h->d_action + b0 * T, h_action + b0 * T, sizeof(float) * nb * T, cudaMemcpyHostToDevice, st));
-            up += sizeof(float) * nb * T;
-        }
-        if (h_yaw) {
+        if (h_yaw)
             CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd + b0 * T, h_yaw + b0 * T, sizeof(double) * nb * T, cudaMemcpyHostToDevice, st));
-            up += sizeof(double) * nb * T;
-        }
         TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st,
                         (int)b0, (int)nb));
 #define D2H(field, per_env)                                                                                       \
     if (ho->field) {                                                                                              \
         const size_t off = b0 * (per_env), bytes = nb * (per_env);                                                \
         CUDA_TRY(cudaMemcpyAsync((char*)ho->field + off, (char*)h->d_out.field + off, bytes, cudaMemcpyDeviceToHost, st)); \
-        down += bytes;                                                                                            \
     }
-        D2H(yaw, T * es) D2H(wind_speed, T * es) D2H(wind_direction, T * es) D2H(power, T * es) D2H(load, 4 * T * es)
+        D2H(load, 4 * T * es) D2H(yaw, T * es) D2H(wind_speed, T * es) D2H(wind_direction, T * es) D2H(power, T * es)
         D2H(reward, es) D2H(freewind, 2 * es) D2H(truncated, 1)
 #undef D2H
     }
-    CUDA_TRY(cudaStreamSynchronize(streams[0]));
-    if (nchunk > 1) CUDA_TRY(cudaStreamSynchronize(streams[1]));
-    if (h2d) *h2d = up;
-    if (d2h) *d2h = down;
+    for (int c = 0; c < nchunk; ++c) CUDA_TRY(cudaStreamSynchronize(h->host_streams[c]));
     return WF_OK;
 }
 
