@@ -14,8 +14,8 @@ own order of operations and numpy dtypes (float32 state/actions, float64 measure
 gymnasium / pettingzoo are not importable here, so spaces are represented by their float32 low/high arrays only.
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU-baseline legs may import this module.  Parity status: the
 env logic below is pinned by the reference notebook's behavioural outputs (spaces ``examples/demo.ipynb:98-99``; 69
-history rows for ``max_num_steps=70`` and the yaw trajectory ``:312-316``); rewards are parity-unpinned (see
-floris_oracle.py).
+history rows for ``max_num_steps=70`` and the yaw trajectory ``:312-316``); rewards and the multi-agent transition are
+pinned by the notebook's printed episode totals and power figures at figure resolution (KAT-3, see floris_oracle.py).
 """
 from __future__ import annotations
 

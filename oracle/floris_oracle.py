@@ -31,10 +31,17 @@ Parity status
 -------------
 * zero-yaw solve, local wind speed / direction: PINNED by the reference's own stored notebook output
   (``examples/demo.ipynb:137-138``, KAT-1; see ``tests/golden/kat1_ablaincourt.json``).
-* per-turbine power: pinned only by a recalled FLORIS-v3 documentation example (KAT-2; not a file in the
-  reference tree).
-* yawed solves, load proxies (TI, std u/v/w), reward: **parity unpinned** by any reference artefact -- only a
-  live FLORIS 3.5 could pin them.  They follow the published algorithm as restated in SURVEY.md App. A.
+* per-turbine power: a recalled FLORIS-v3 documentation example (KAT-2; not a file in the reference tree) and, from
+  the reference's own artefacts, KAT-3 below.
+* yawed solves (down to the -40 deg bound), farm power, reward incl. the load-proxy term, single- and multi-agent
+  transition logic: PINNED AT FIGURE RESOLUTION by KAT-3 (``tests/golden/kat3_notebook_curves.json``,
+  ``tools/make_golden_curves.py``, ``tests/test_notebook_curves.py``): the farm-power curves FLORIS 3.5 produced for the
+  two yawing episodes of ``examples/demo.ipynb`` (stored PNG outputs, digitised at 7.5e-4 / 4.3e-3 MW per pixel) and the
+  printed episode totals (189.31593162, 192.22698147).  The winds of those episodes are not stored, so two numbers
+  per episode are fitted; with them this oracle reproduces all 14 / 17 plateau levels within 0.27 / 0.23 pixel
+  (2e-4 / 1e-3 MW, i.e. 2e-5 / 1e-4 of the farm power) AND the printed totals within 2.8e-6 / 4.2e-6 relative at the same
+  time.  What stays unpinned beyond that resolution: per-turbine values of yawed solves and the individual load proxies
+  (they enter the totals only as a 0.7 % term) -- only a live FLORIS 3.5 could pin those digit for digit.
 """
 from __future__ import annotations
 
