@@ -90,3 +90,29 @@ def test_cuda_fp32_batch_reproduces_notebook_single_agent_curve(cuda_device):
     assert bool(trunc.all())
     _check("single_agent", total, np.array(power), total_rtol=1e-4)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,total_rtol", [("f64", 1e-5), ("f32", 1e-4)])
+def test_cuda_batched_multi_agent_env_reproduces_notebook_curve(cuda_device, precision, total_rtol):
+    """The decentralised episode (yaw down to the -40 deg bound) through the BATCHED multi-agent env: one call per agent
+    cycle, the stale per-agent actuation constraint evaluated inside the kernel."""
+    import torch
+
+    from wfcrl_b200 import environments as envs
+
+    g = GOLD["multi_agent"]
+    env = envs.make_vec("Dec_Ablaincourt_Floris", 3, precision=precision, max_num_steps=70, auto_reset=False)
+    env.reset(options={"wind_speed": g["fitted_wind_speed"], "wind_direction": g["fitted_wind_direction"]})
+    total, power = 0.0, []
+    for cycle in range(69):
+        a = torch.zeros(3, 7, device="cuda")
+        for j in range(7):
+            if cycle % (4 * (j + 1)) == 0:
+                a[:, j] = -5.0
+        _obs, reward, _term, trunc, info = env.step(a)
+        total += float(reward["turbine_1"][1])
+        power.append(float(sum(info[agent]["power"][1] for agent in env.possible_agents)))
+    assert bool(trunc["turbine_7"].all())
+    _check("multi_agent", total, np.array(power), total_rtol=total_rtol)
+    env.close()
