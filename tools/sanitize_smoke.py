@@ -8,7 +8,7 @@ from wfcrl_b200.backend import FlorisBatch
 from wfcrl_b200.layouts import layout_xy
 
 for name, prec, kern in (("Turb6_Row2_", "f64", "basic"), ("Ablaincourt_", "f32", "fast"), ("HornsRev1_", "f32", "fast"),
-                         ("HornsRev2_", "f32", "fast")):
+                         ("HornsRev2_", "f32", "fast"), ("Turb32_Row5_", "f64", "fast")):
     lx, ly = layout_xy(name)
     B, T = 6, len(lx)
     fb = FlorisBatch(lx, ly, B, precision=prec, kernel=kern, max_iter=5)
@@ -19,7 +19,14 @@ for name, prec, kern in (("Turb6_Row2_", "f64", "basic"), ("Ablaincourt_", "f32"
     mask = out["truncated"].clone()
     fb.reset_masked(mask, torch.full((B,), 9.0, dtype=torch.float64, device="cuda"),
                     torch.full((B,), 265.0, dtype=torch.float64, device="cuda"))
-    fb.step_host(torch.zeros(B, T).pin_memory())
+    fb.reset_sampled(mask, seed=7, env_id_offset=3, turbulence_intensity_range=(0.04, 0.12))
+    yaw = torch.zeros(B, T, device="cuda")
+    yaw[:, ::2] = 7.0  # mixed yawed / unyawed sources
+    fb.update_command(yaw.double())
+    fb.step_host(torch.zeros(B, T).pin_memory())          # zero-copy route (mapped pinned buffers)
+    os.environ["WFCRL_B200_HOST_PATH"] = "staged"
+    fb.step_host(torch.zeros(B, T).pin_memory())          # staged route (copy engines)
+    del os.environ["WFCRL_B200_HOST_PATH"]
     torch.cuda.synchronize()
     print(name, prec, kern, "ok", float(out["reward"].sum()))
     fb.close()
