@@ -264,6 +264,10 @@ def run_ours(args):
             os.close(saved)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from wfcrl_b200.dist import bind_to_gpu_numa_node
+
+    all_cpus = os.sched_getaffinity(0)  # restored before the CPU baseline, which wants every host core
+    numa = bind_to_gpu_numa_node(local) if not os.environ.get("WFCRL_NO_NUMA_BIND") else {"bound": False}
 
     case = get_layout(LAYOUT)
     T, B = case["num_turbines"], args.envs_per_gpu
@@ -352,6 +356,7 @@ def run_ours(args):
     os.environ["WFCRL_B200_HOST_PATH"] = "zero_copy"  # same call with the pinned buffers mapped into the step kernel
     e2e_zero_s = e2e_run()
     del os.environ["WFCRL_B200_HOST_PATH"]
+    os.sched_setaffinity(0, all_cpus)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------------
     stats = torch.tensor([total_ms, e2e_s, e2e_zero_s], dtype=torch.float64, device=dev)
@@ -423,6 +428,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "path": "FlorisBatch.step_host -> wf_step_host (pinned HOST action in, full step result out): "
                             "6 env chunks, one stream each, H2D + kernel + D2H per chunk",
+                    "host_numa_binding": numa,
                     "zero_copy_value": world * B * e2e_steps / e2e_zero_s,
                     "zero_copy_path": "same call with WFCRL_B200_HOST_PATH=zero_copy: host buffers mapped into the step "
                                       "kernel, one launch, no copy engine (the library's default up to 163840 env x "

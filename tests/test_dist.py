@@ -52,3 +52,14 @@ def test_gather_episode_stats_gloo_world2():
 def test_single_process_stats():
     stats = gather_episode_stats(torch.tensor([1.0, 3.0]), torch.tensor([5, 7]))
     assert stats == {"episodes": 2.0, "return_mean": 2.0, "return_std": 1.0, "length_mean": 6.0, "world_size": 1}
+
+
+def test_numa_binding_helper_is_best_effort():
+    from wfcrl_b200.dist import _parse_cpulist, bind_to_gpu_numa_node
+
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and _parse_cpulist("") == []
+    import os
+
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa_node(0, sysfs="/nonexistent")   # no GPU / no sysfs entry: reports, never raises
+    assert info["bound"] is False and "error" in info and os.sched_getaffinity(0) == before

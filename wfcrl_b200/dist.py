@@ -40,3 +40,40 @@ def gather_episode_stats(returns: torch.Tensor, lengths: torch.Tensor) -> Dict[s
     var = max(ss / n - mean * mean, 0.0) if n else float("nan")
     return {"episodes": n, "return_mean": mean, "return_std": var ** 0.5 if n else float("nan"),
             "length_mean": ln / n if n else float("nan"), "world_size": size}
+
+
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device: int = 0, sysfs: str = "/sys/bus/pci/devices") -> Dict[str, object]:
+    """Pin the calling process to the CPUs that are local to ``cuda:device`` (its PCIe root's NUMA node), so that pinned
+    host buffers allocated afterwards are NUMA-local to the GPU that reads and writes them.  On a multi-socket 8-GPU box
+    the host-buffer path (``wf_step_host``) otherwise pushes half of its traffic across the socket interconnect.
+    Best effort: returns what was done; never raises."""
+    import os
+
+    info: Dict[str, object] = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, bdf, "local_cpulist")) as fp:
+            cpus = _parse_cpulist(fp.read())
+        try:
+            with open(os.path.join(sysfs, bdf, "numa_node")) as fp:
+                info["numa_node"] = int(fp.read().strip())
+        except OSError:
+            pass
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed), pci=bdf)
+    except Exception as exc:  # noqa: BLE001 - best effort by design
+        info["error"] = repr(exc)
+    return info
