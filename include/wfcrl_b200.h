@@ -147,6 +147,8 @@ int wf_reset_sampled(WfHandle h, const uint8_t* d_mask, uint64_t seed, int64_t e
  * (mdp.py:291-319), FlorisInterface.update_command (interface.py:557-586), powers/1e6 and loads/1e7
  * (mdp.py:278-284), reward with the previous state's free-stream speed (simple_env.py:78-85) and the shaper.
  *   d_action: DEVICE float [B][T]; continuous: yaw increments in degrees; discrete: values in {0,1,2}.
+ * A pure stream operation (one kernel launch, no host synchronisation, no allocation): it can be captured into a CUDA
+ * graph together with the caller's own kernels (wf_launch_count then counts the captured launch once).
  */
 int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream);
 

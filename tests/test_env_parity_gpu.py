@@ -271,3 +271,42 @@ def test_nonfinite_guard_counter(cuda_device):
     torch.cuda.synchronize()
     assert list(fb.get_state("nonfinite")) == [0, 1] and not bool(torch.isfinite(out["reward"][1]))
     fb.close()
+
+
+def test_step_is_cuda_graph_capturable(cuda_device):
+    """wf_step is a pure stream operation (no host sync, no allocation): a captured graph of several env steps replays
+    to the same bits as eager launches -- the way to drive small layouts, where launch overhead is the step time."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Ablaincourt_")
+    B, T, K = 64, len(lx), 4
+    ws, wd = sample_winds(B, seed=4)
+    eager = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=1000)
+    graphed = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=1000)
+    for f in (eager, graphed):
+        f.reset(ws, wd, host_trig=False)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    actions = [torch.rand(B, T, device="cuda", generator=gen) * 10 - 5 for _ in range(K)]
+    static = [a.clone() for a in actions]
+    rewards = torch.zeros(K, B, device="cuda")
+    graphed.step(static[0])          # warm-up outside capture (lazy function attributes)
+    eager.step(actions[0])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(K):
+            out = graphed.step(static[k])
+            rewards[k].copy_(out["reward"])
+    for rep in range(2):             # two replays = 2 K further env steps
+        g.replay()
+        want = []
+        for k in range(K):
+            want.append(eager.step(actions[k])["reward"].clone())
+        torch.cuda.synchronize()
+        assert torch.equal(rewards, torch.stack(want)), rep
+    assert torch.equal(graphed.out["yaw"], eager.out["yaw"])
+    assert np.array_equal(graphed.get_state("num_iter"), eager.get_state("num_iter"))
+    eager.close()
+    graphed.close()
