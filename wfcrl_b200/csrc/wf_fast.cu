@@ -12,6 +12,7 @@
 //      2. V sweep over ALL downstream targets, 10 turbines x 3 lateral grid columns per pass (30 of 32 lanes), each lane
 //         doing the 3 vertical points of its column: the three vortex pairs (real + ground mirror) and the (v, w)
 //         update; the same pass ballots a compacted queue of the targets that can see the velocity deficit;
+//         a source at exactly zero yaw sheds no tip vortices and runs an instantiation with the wake-rotation pair only;
 //      3. D sweep over the queue only: deflection, wake widths, Gaussian deficit, sum-of-squares update, overlap count
 //         and wake-added turbulence.
 //  * x-direction masks are NOT evaluated in floating point here: the geometry kernel (FP64) stores, per source, the
