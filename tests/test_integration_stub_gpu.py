@@ -40,3 +40,32 @@ def test_integration_md_stub_runs_and_matches_oracle(cuda_device):
     assert iface.get_measure("pitch") is None and np.allclose(iface.get_measure("freewind_measurements"), [6.48958384, 266.363907])
     iface.update_command()
     assert iface.update_command() is True  # 4th iteration == max_iter
+
+
+def test_plain_c_client_of_the_abi(cuda_device, tmp_path):
+    """examples/c_abi_example.c: a C program with no Python / torch in the process drives the library through the
+    host-buffer entry points and prints the reference notebook's reset observation (KAT-1) and one env step."""
+    import subprocess
+
+    from wfcrl_b200 import _lib
+
+    libdir = os.path.dirname(_lib.library_path())
+    exe = str(tmp_path / "c_abi_example")
+    subprocess.run(["gcc", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_example.c"),
+                    "-L" + libdir, "-lwfcrl_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    text = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    rows = {line.split(":")[0]: line.split(":", 1)[1] for line in text.strip().splitlines()}
+    ws_l = np.array(rows["local wind speed"].split(), dtype=float)
+    wd_l = np.array(rows["local wind direction"].split(), dtype=float)
+    assert np.max(np.abs(ws_l - [6.46819497, 4.58929161, 6.46702757, 6.21243961, 6.20072934, 6.1100638, 5.76785291])) < 2e-8
+    assert np.max(np.abs(wd_l - [266.64538262, 267.04575667, 266.77944635, 266.86120544, 266.89071421, 266.92108378,
+                                 266.99680007])) < 2e-8
+    assert rows["yaw after step"].split() == ["-5.0"] + ["0.0"] * 6
+    lx, ly = layout("Ablaincourt_")
+    ref = c_oracle.solve(lx, ly, 6.48958384, 266.363907, np.array([-5.0, 0, 0, 0, 0, 0, 0]))
+    power = np.array(rows["power MW"].split(), dtype=float)
+    assert np.max(np.abs(power - ref.power_W / 1e6) / (ref.power_W / 1e6)) < 1e-8      # printed with 9 decimals
+    loads = np.stack([ref.ti, ref.std_u, ref.std_v, ref.std_w], 1)
+    reward = np.mean(ref.power_W / 1e6 * 1e3 / 6.48958384 ** 3) - 0.1 * np.mean(np.abs(loads))
+    got = float(rows["reward"].split()[0])
+    assert abs(got - reward) < 1e-9 * abs(reward) and "truncated: 0" in text
