@@ -340,12 +340,12 @@ def run_ours(args):
     host_pool = [p.cpu().pin_memory() for p in pool[:4]]
     e2e_steps = max(3, min(args.steps, 50))
 
-    def e2e_run():
-        fb.step_host(host_pool[0])
+    def e2e_run(**kw):
+        fb.step_host(host_pool[0], **kw)
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
-            res = fb.step_host(host_pool[k % len(host_pool)])
+            res = fb.step_host(host_pool[k % len(host_pool)], **kw)
         barrier()
         dt = time.perf_counter() - t0
         assert bool(torch.isfinite(res["reward"]).all())
@@ -356,10 +356,13 @@ def run_ours(args):
     os.environ["WFCRL_B200_HOST_PATH"] = "zero_copy"  # same call with the pinned buffers mapped into the step kernel
     e2e_zero_s = e2e_run()
     del os.environ["WFCRL_B200_HOST_PATH"]
+    # what a policy consumes per step (observation + reward + flag), without the info arrays power / load
+    e2e_obs_s = e2e_run(fields=("yaw", "wind_speed", "wind_direction", "freewind", "reward", "truncated"))
+    d2h_obs = fb.last_d2h_bytes
     os.sched_setaffinity(0, all_cpus)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------------
-    stats = torch.tensor([total_ms, e2e_s, e2e_zero_s], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, e2e_s, e2e_zero_s, e2e_obs_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         # the only collective of the job: all-gather of per-rank episode-return statistics (north_star)
@@ -369,7 +372,7 @@ def run_ours(args):
         mean_return = float(torch.stack(gathered)[:, 0].mean())
     else:
         mean_return = float(returns.mean())
-    total_ms, e2e_s, e2e_zero_s = float(stats[0]), float(stats[1]), float(stats[2])
+    total_ms, e2e_s, e2e_zero_s, e2e_obs_s = (float(v) for v in stats)
 
     if rank == 0:
         info = fb.device_info()
@@ -429,6 +432,8 @@ def run_ours(args):
                     "path": "FlorisBatch.step_host -> wf_step_host (pinned HOST action in, full step result out): "
                             "6 env chunks, one stream each, H2D + kernel + D2H per chunk",
                     "host_numa_binding": numa,
+                    "observation_only_value": world * B * e2e_steps / e2e_obs_s,
+                    "observation_only_d2h_bytes_per_step": int(d2h_obs),
                     "zero_copy_value": world * B * e2e_steps / e2e_zero_s,
                     "zero_copy_path": "same call with WFCRL_B200_HOST_PATH=zero_copy: host buffers mapped into the step "
                                       "kernel, one launch, no copy engine (the library's default up to 163840 env x "
