@@ -61,15 +61,24 @@ class FlorisInterface(BaseInterface):
                  wind_speed: float = None, wind_direction: float = None,
                  wind_time_series: Union[str, np.ndarray] = None, *, xcoords=None, ycoords=None, device: int = 0,
                  precision: str = "f64", kernel: str = "fast"):
-        """``simul_file`` (the FLORIS yaml of the reference) may be a dict with ``xcoords``/``ycoords`` or None when the
-        coordinates are passed by keyword; the flow/wake parameters are the template's (case.yaml), baked into the
-        library's default config."""
+        """``simul_file``: path of a FLORIS v3 input yaml as in the reference (layout, flow field and Gauss / GCH /
+        Crespo-Hernandez parameters are read from it; models the kernels do not implement are refused, see
+        ``floris_yaml.py``), or a dict with ``xcoords``/``ycoords``, or None when the coordinates are passed by keyword
+        (flow / wake parameters then are the template's, wfcrl/simulators/floris/inputs/template/case.yaml)."""
         super().__init__()
         import torch
 
         from .backend import FlorisBatch
 
-        if isinstance(simul_file, dict):
+        overrides = None
+        if isinstance(simul_file, str):
+            from .floris_yaml import load_floris_yaml
+
+            parsed = load_floris_yaml(simul_file)
+            xcoords, ycoords, overrides = parsed["xcoords"], parsed["ycoords"], parsed["overrides"]
+            wind_speed = parsed["wind_speed"] if wind_speed is None else wind_speed
+            wind_direction = parsed["wind_direction"] if wind_direction is None else wind_direction
+        elif isinstance(simul_file, dict):
             xcoords, ycoords = simul_file["xcoords"], simul_file["ycoords"]
         if xcoords is None or ycoords is None:
             raise ValueError("FlorisInterface needs the turbine coordinates (xcoords, ycoords)")
@@ -77,7 +86,7 @@ class FlorisInterface(BaseInterface):
         self.num_turbines = num_turbines
         self._torch = torch
         self.fi = FlorisBatch(xcoords, ycoords, 1, device=device, precision=precision, kernel=kernel,
-                              max_iter=int(max_iter))
+                              max_iter=int(max_iter), config_overrides=overrides)
         self.measure_map = self.DEFAULT_MEASURE_MAP
         self._num_measures = 7
         self.dt = 60
