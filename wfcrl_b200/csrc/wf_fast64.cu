@@ -269,7 +269,6 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
 
         // ===== V sweep =====
         int qn = 0;
-        const bool yawed = (Gt != 0.0) || (Gb != 0.0);
         for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
             const int tr = t0 + g;
             const bool active = lane_ok && tr < T && tr != i;
@@ -291,31 +290,21 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {  // not unrolled: keeps the FP64 kernel inside the instruction cache
                 // pairs (real a, ground mirror b): (0,2) top, (1,3) bottom, (4,5) wake rotation
+                const double r0 = q + fc.zz2[0][k], r2 = q + fc.zz2[2][k], r1 = q + fc.zz2[1][k], r3 = q + fc.zz2[3][k];
                 const double r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
-                const double p45 = r4 * r5, dd = fc.nu4[k] * dx + eps2;
+                // ONE division for the three pair denominators and the downstream decay (products stay < 1e60)
+                const double p02 = r0 * r2, p13 = r1 * r3, p45 = r4 * r5, dd = fc.nu4[k] * dx + eps2;
+                const double P = p02 * p13, Q = p45 * dd;
+                const double inv = 1.0 / (P * Q);
+                const double iP = inv * Q, iQ = inv * P;
+                const double g0 = Gt * (iP * p13), g1 = Gb * (iP * p02), g4 = Gwr * (iQ * dd);
+                const double dec = c_dec * (iQ * p45);
+                const double Xa0 = (1.0 - E * fc.ez[0][k]) * r2, Xb0 = (1.0 - E * fc.ez[2][k]) * r0;
+                const double Xa1 = (1.0 - E * fc.ez[1][k]) * r3, Xb1 = (1.0 - E * fc.ez[3][k]) * r1;
                 const double Xa4 = (1.0 - E * fc.ez[4][k]) * r5, Xb4 = (1.0 - E * fc.ez[5][k]) * r4;
-                const double NV4 = fc.zz[4][k] * Xa4 - fc.zz[5][k] * Xb4, NW4 = Xa4 - Xb4;
-                double SV, SW, dec;
-                if (yawed) {  // warp-uniform
-                    const double r0 = q + fc.zz2[0][k], r2 = q + fc.zz2[2][k], r1 = q + fc.zz2[1][k], r3 = q + fc.zz2[3][k];
-                    // ONE division for the three pair denominators and the downstream decay (products stay < 1e60)
-                    const double p02 = r0 * r2, p13 = r1 * r3;
-                    const double P = p02 * p13, Q = p45 * dd;
-                    const double inv = 1.0 / (P * Q);
-                    const double iP = inv * Q, iQ = inv * P;
-                    const double g0 = Gt * (iP * p13), g1 = Gb * (iP * p02), g4 = Gwr * (iQ * dd);
-                    dec = c_dec * (iQ * p45);
-                    const double Xa0 = (1.0 - E * fc.ez[0][k]) * r2, Xb0 = (1.0 - E * fc.ez[2][k]) * r0;
-                    const double Xa1 = (1.0 - E * fc.ez[1][k]) * r3, Xb1 = (1.0 - E * fc.ez[3][k]) * r1;
-                    SV = g0 * (fc.zz[0][k] * Xa0 - fc.zz[2][k] * Xb0) + g1 * (fc.zz[1][k] * Xa1 - fc.zz[3][k] * Xb1) + g4 * NV4;
-                    SW = g0 * (Xa0 - Xb0) + g1 * (Xa1 - Xb1) + g4 * NW4;
-                } else {      // zero yaw sheds no tip vortices: wake-rotation pair only
-                    const double inv = 1.0 / (p45 * dd);
-                    const double g4 = Gwr * (inv * dd);
-                    dec = c_dec * (inv * p45);
-                    SV = g4 * NV4;
-                    SW = g4 * NW4;
-                }
+                const double SV = g0 * (fc.zz[0][k] * Xa0 - fc.zz[2][k] * Xb0) + g1 * (fc.zz[1][k] * Xa1 - fc.zz[3][k] * Xb1) +
+                                  g4 * (fc.zz[4][k] * Xa4 - fc.zz[5][k] * Xb4);
+                const double SW = g0 * (Xa0 - Xb0) + g1 * (Xa1 - Xb1) + g4 * (Xa4 - Xb4);
                 Vk[k] = SV * dec;
                 Wk[k] = fmax(SW * (-yL * dec), 0.0);
             }
