@@ -16,18 +16,28 @@ local = int(os.environ.get("LOCAL_RANK", 0))
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-total_envs, steps = 8192 * world, 600
+total_envs = int(os.environ.get("WFCRL_TOTAL_ENVS", 8192 * world))  # fixed total: N-GPU runs reproduce the 1-GPU episodes
+steps = int(os.environ.get("WFCRL_STEPS", 600))
 lo, hi = shard_range(total_envs, rank, world)
 env = envs.make_vec("HornsRev1_Floris", hi - lo, device=local, precision="f32", max_num_steps=500, env_id_offset=lo)
 obs = env.reset(seed=0)
 policy_gain = -0.05  # toy proportional policy: steer every turbine back towards zero yaw, plus exploration noise
-for k in range(10):  # warm-up (lazy CUDA / RNG initialisation)
-    obs, *_ = env.step(policy_gain * obs["yaw"] + torch.randn_like(obs["yaw"]))
+gids = torch.arange(lo, hi, device=obs["yaw"].device, dtype=torch.float64)[:, None]
+cols = torch.arange(obs["yaw"].shape[1], device=obs["yaw"].device, dtype=torch.float64)[None, :]
+
+
+def noise(k):
+    """Exploration noise in [-2, 2) as a function of (global env id, turbine, step): identical however the batch is
+    sharded over ranks, so an N-GPU run reproduces the single-GPU episodes."""
+    return torch.sin(12.9898 * gids + 78.233 * cols + 37.719 * k).mul(43758.5453).frac().float() * 4 - 2
+
+
+for k in range(-10, 0):  # warm-up (lazy CUDA initialisation)
+    obs, *_ = env.step(policy_gain * obs["yaw"] + noise(k))
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for k in range(steps):
-    action = policy_gain * obs["yaw"] + torch.randn_like(obs["yaw"])
-    obs, reward, terminated, truncated, info = env.step(action)
+    obs, reward, terminated, truncated, info = env.step(policy_gain * obs["yaw"] + noise(k))
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 stats = env.episode_statistics()  # the only collective: all-gather of 4 doubles per rank
