@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+// Relative half-width of the FP32 kernel's guard band around the 0.05 m/s overlap threshold.
+static constexpr float kDefaultAmbEps = 2e-5f;
+
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
     g_err = msg;
@@ -48,6 +51,8 @@ struct WfHandle_t {
     static constexpr int kHostStreams = 6;
     cudaStream_t host_streams[kHostStreams] = {};  // one per chunk of the wf_step_host pipeline
     uint64_t launches = 0;
+    bool vtab_stale = false;  // some env's vortex-table rows do not match its geometry: launch the kernels that ignore the table
+    uint64_t steps_since_wind_update = 1u << 30;  // wf_update_wind rebuilds the vortex table only when it is not called every step
 };
 
 template <typename T> static int dev_alloc(WfHandle_t* h, T** p, size_t n) {
@@ -65,6 +70,21 @@ template <typename T> static int dev_alloc(WfHandle_t* h, T** p, size_t n) {
         int _r = (expr);          \
         if (_r != WF_OK) return _r; \
     } while (0)
+
+// rotated + sorted geometry of the selected envs and, unless told otherwise, their vortex-table rows
+static cudaError_t launch_geometry(WfHandle h, const uint8_t* d_mask, const double* d_cs, cudaStream_t st,
+                                   bool build_table = true) {
+    cudaError_t e = wf_launch_geometry(h->model, h->st, d_mask, d_cs, st);
+    h->launches += 1;
+    if (e == cudaSuccess && build_table && h->st.vtab) {
+        e = wf_launch_vortex_table(h->cfg.precision, h->model, h->fast64, h->st, d_mask, st);
+        h->launches += 1;
+        if (!d_mask) h->vtab_stale = false;
+    } else if (h->st.vtab) {
+        h->vtab_stale = true;
+    }
+    return e;
+}
 
 
 extern "C" {
@@ -136,6 +156,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     m.shaper = cfg->reward_shaper; m.table_len = cfg->table_len;
     m.yaw_lo_f = (float)cfg->yaw_lo; m.yaw_hi_f = (float)cfg->yaw_hi; m.yaw_step_f = (float)cfg->yaw_step;
     m.rate_f = (float)cfg->actuator_rate; m.dt_f = (float)cfg->dt;
+    m.amb_eps = getenv("WFCRL_B200_AMB_EPS") ? (float)atof(getenv("WFCRL_B200_AMB_EPS")) : kDefaultAmbEps;
     m.load_coef = cfg->load_coef; m.shaper_reference = cfg->shaper_reference;
     m.rho = cfg->air_density; m.ref_rho = cfg->ref_density_cp_ct; m.shear = cfg->wind_shear;
     m.D = cfg->rotor_diameter; m.HH = cfg->hub_height; m.TSR = cfg->tsr; m.pP = cfg->pP;
@@ -178,7 +199,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     const size_t BT = (size_t)B * T;
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
-        (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) || (rc = dev_alloc(h, &s.amb, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -188,6 +209,24 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         (rc = dev_alloc(h, &h->d_rws, (size_t)B)) || (rc = dev_alloc(h, &h->d_rwd, (size_t)B)) ||
         (rc = dev_alloc(h, &h->d_rcs, (size_t)2 * B)))
         return fail(rc);
+    if ((rc = dev_alloc(h, &s.tab_lo, BT))) return fail(rc);
+    if (cfg->kernel == WF_KERNEL_FAST && T >= 2 && !getenv("WFCRL_B200_NO_VTAB")) {
+        // vortex table (wf_device.cuh): 36 reals per sorted turbine pair and env; skipped when it would not fit comfortably
+        const size_t bytes = (size_t)B * ((size_t)T * (T - 1) / 2) * 36 * h->es;
+        const size_t cap = (size_t)(getenv("WFCRL_B200_VTAB_MAX_MB") ? atof(getenv("WFCRL_B200_VTAB_MAX_MB")) : 24576.0) << 20;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes <= cap && bytes <= free_b / 2) {
+            void* p = nullptr;
+            if (cudaMalloc(&p, bytes) == cudaSuccess) {
+                h->allocs.push_back(p);
+                s.vtab = p;
+                if ((rc = dev_alloc(h, &s.vtab_ok, (size_t)B))) return fail(rc);
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     if (cudaMallocHost((void**)&h->h_mask, B) != cudaSuccess || cudaMallocHost((void**)&h->h_rws, sizeof(double) * B) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_rwd, sizeof(double) * B) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_rcs, sizeof(double) * 2 * B) != cudaSuccess)
@@ -203,8 +242,8 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         cudaMemcpy(h->d_rwd, wd.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
         cudaMemcpy(s.ti_amb, ti.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
         cudaError_t e1 = wf_launch_reset_state(m, s, nullptr, h->d_rws, h->d_rwd, 0);
-        cudaError_t e2 = wf_launch_geometry(m, s, nullptr, nullptr, 0);
-        h->launches += 2;
+        cudaError_t e2 = launch_geometry(h, nullptr, nullptr, 0);
+        h->launches += 1;
         cudaError_t e3 = cudaDeviceSynchronize();
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
             return fail(set_err(WF_ERR_CUDA, std::string("init kernels failed: ") +
@@ -228,14 +267,15 @@ static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float*
     if (env_count < 0) env_count = h->model.B;
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64)
-        e = wf_launch_step_fast64(mode, h->model, h->fast64, h->st, d_mask, d_action, d_yaw, out, env_begin, env_count, st);
+        e = wf_launch_step_fast64(mode, !h->vtab_stale, h->model, h->fast64, h->st, d_mask, d_action, d_yaw, out, env_begin, env_count, st);
     else if (h->cfg.kernel == WF_KERNEL_FAST)
-        e = wf_launch_step_fast(mode, h->fast_baked, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
+        e = wf_launch_step_fast(mode, h->fast_baked, !h->vtab_stale, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
                                 env_count, st);
     else
         e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, env_begin,
                                  env_count, st);
     h->launches += 1;
+    h->steps_since_wind_update += 1;
     if (e != cudaSuccess) return set_err(WF_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
     return WF_OK;
 }
@@ -246,8 +286,8 @@ int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(wf_launch_reset_state(h->model, h->st, d_mask, d_ws, d_wd, st));
-    CUDA_TRY(wf_launch_geometry(h->model, h->st, d_mask, nullptr, st));
-    h->launches += 2;
+    CUDA_TRY(launch_geometry(h, d_mask, nullptr, st));
+    h->launches += 1;
     for (int k = 0; k < warmup; ++k) TRY(launch_step(h, WF_MODE_WARMUP, d_mask, nullptr, nullptr, to_ptrs(out), st));
     return WF_OK;
 }
@@ -287,8 +327,8 @@ int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const 
     CUDA_TRY(cudaMemcpyAsync(h->d_rwd, h->h_rwd, sizeof(double) * B, cudaMemcpyHostToDevice, st));
     if (hc) CUDA_TRY(cudaMemcpyAsync(h->d_rcs, h->h_rcs, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, st));
     CUDA_TRY(wf_launch_reset_state(h->model, h->st, h->d_mask, h->d_rws, h->d_rwd, st));
-    CUDA_TRY(wf_launch_geometry(h->model, h->st, h->d_mask, hc ? h->d_rcs : nullptr, st));
-    h->launches += 2;
+    CUDA_TRY(launch_geometry(h, h->d_mask, hc ? h->d_rcs : nullptr, st));
+    h->launches += 1;
     for (int k = 0; k < warmup; ++k)
         TRY(launch_step(h, WF_MODE_WARMUP, h->d_mask, nullptr, nullptr, to_ptrs(out), st));
     CUDA_TRY(cudaStreamSynchronize(st));  // the handle-owned pinned staging is reusable when this call returns
@@ -427,8 +467,12 @@ int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const 
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(wf_launch_set_wind(h->model, h->st, d_mask, d_ws, d_wd, st));
-    CUDA_TRY(wf_launch_geometry(h->model, h->st, d_mask, d_cs, st));
-    h->launches += 2;
+    // Time-series mode moves the wind before every step (interface.py:563): rebuilding the table each time would cost
+    // more than it saves, so it is rebuilt only when the wind has been steady for a while (restore, occasional updates);
+    // envs without valid rows take the step kernel's direct path.
+    CUDA_TRY(launch_geometry(h, d_mask, d_cs, st, h->steps_since_wind_update >= 8));
+    h->launches += 1;
+    h->steps_since_wind_update = 0;
     return WF_OK;
 }
 
@@ -445,7 +489,7 @@ static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
     const WfState& s = h->st;
     struct { const char* n; void* p; size_t b; } tab[] = {
         {"yaw", s.yaw, BT * 8}, {"acc", s.acc, BT * 4}, {"acc_prev", s.acc_prev, BT * 4},
-        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"episode", s.episode, B * 4}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
+        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"episode", s.episode, B * 4}, {"ambiguous", s.amb, B}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
         {"ws_norm", s.ws_norm, B * 8}, {"shaper_ref", s.shaper_ref, B * 8}, {"ti_ambient", s.ti_amb, B * 8},
         {"order", s.order, BT * 4}, {"xs", s.xs, BT * 8}, {"ys", s.ys, BT * 8}, {"xi", s.xi, BT * 8},
         {"yi", s.yi, BT * 8}, {"cs", s.cs, B * 16}};
@@ -485,7 +529,7 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64) {
         CUDA_TRY(wf_step_fast64_attributes(h->model, &attr, &ctas, &thr, &sm));
     } else if (h->cfg.kernel == WF_KERNEL_FAST) {
-        CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->model, &attr, &ctas, &thr, &sm));
+        CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->st.vtab && !h->vtab_stale, h->model, &attr, &ctas, &thr, &sm));
     } else {
         CUDA_TRY(wf_step_basic_attributes(h->cfg.precision, &attr, &ctas, thr));
         sm = (int)attr.sharedSizeBytes;

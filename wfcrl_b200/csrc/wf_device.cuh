@@ -12,6 +12,7 @@ struct WfModel {
     int max_iter, continuous, multi_agent, shaper, table_len;
     float yaw_lo_f, yaw_hi_f, yaw_step_f;  // float32 bounds exactly as gymnasium Box stores them (mdp.py:111-116,143-144)
     float rate_f, dt_f;
+    float amb_eps;                 // relative half-width of the guard band around the 0.05 m/s overlap threshold (FP32 kernel)
     double load_coef, shaper_reference;
     double rho, ref_rho, shear, D, HH, TSR, pP;
     double alpha, beta, ka, kb, ad, bd, dm;
@@ -34,6 +35,8 @@ struct WfState {
     int* num_moves;     // [B] WindFarmEnv.num_moves
     int* nonfinite;     // [B] number of env steps whose reward came out NaN/Inf (guard counter)
     int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
+    uint8_t* amb;       // [B] FP32 kernel: 1 = a discrete decision of this solve was within the guard band of its threshold
+                        //     AND could change the result (the env is re-solved by the FP64 kernel), 0 = decisions are safe
     double* ws;         // [B] free-stream wind speed
     double* wd;         // [B] free-stream wind direction (already % 360)
     double* ws_norm;    // [B] free-stream speed of the PREVIOUS state (reward normalisation, simple_env.py:79)
@@ -52,6 +55,16 @@ struct WfState {
     float2* yhl;        // [B][T] (hi, lo) of ys - yc
     uchar4* idx;        // [B][T] .x: first t with X[t]-x_i >= 0 ; .y: first t with X[t] > x_i+0.1 ;
                         //         .z: first t with X[t] > x_i ; .w: first t with X[t] > x_i+15D   (T if none)
+    // Vortex table (warp-per-env kernels): the transverse velocities one source induces on one rotor point are LINEAR in
+    // the source's two circulations (tip pair Gt -- the bottom tip vortex is -vel_bot/vel_top times the top one -- and
+    // wake rotation Gwr) with coefficients that depend on the geometry only.  Built once per wind direction by
+    // wf_vortex_table_kernel in SORTED order, so that the step kernel streams it front to back:
+    //   row(i, t) for sorted source i < target t at index i*T - i*(i+1)/2 + (t - i - 1); a row is [3 columns j][3 heights k]
+    //   [cVt, cVw, cWt, cWw]:  V += Gt*cVt + Gwr*cVw ;  W += max(Gt*cWt + Gwr*cWw, 0)            
+    void* vtab;         // [B][T(T-1)/2][36] float (FP32 handle) or double (FP64 handle); NULL = table disabled
+    uint8_t* vtab_ok;   // [B] 1 = the env's rows match its current geometry (cleared by the geometry kernel)
+    uint8_t* tab_lo;    // [B][T] per sorted source i: first t with xs[t] - xs[i] > 1e-6 m; closer targets (x-ties) are
+                        //         evaluated directly from the positions, never through the table
 };
 
 // Constants of the tuned warp-per-env kernels, precomputed on the host in FP64 (wf_host_const.h: build_fast_const);
@@ -103,6 +116,8 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
                                  int env_begin, int env_count, cudaStream_t stream);
+cudaError_t wf_launch_vortex_table(int precision, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                                   const uint8_t* d_mask, cudaStream_t stream);
 cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                const double* d_wd, cudaStream_t stream);
 cudaError_t wf_launch_sample_reset(const WfModel& m, const WfState& s, const uint8_t* d_mask, unsigned long long seed,
@@ -111,12 +126,12 @@ cudaError_t wf_launch_sample_reset(const WfModel& m, const WfState& s, const uin
 cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                   const double* d_wd, cudaStream_t stream);
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);
-cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
+cudaError_t wf_launch_step_fast(int mode, bool baked, bool use_vtab, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                 const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
-cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+cudaError_t wf_step_fast_attributes(bool baked, bool use_vtab, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);
-cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                   const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
 cudaError_t wf_step_fast64_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,

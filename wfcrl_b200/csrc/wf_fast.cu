@@ -44,6 +44,7 @@ constexpr float kDeg = 57.29577951308232f;
 constexpr float kRad = 0.017453292519943295f;
 constexpr float kNumEpsF = 0.001f;
 constexpr int kTurbPerPass = 10;
+constexpr int kMaxEvt = 8;  // ambiguous-decision records kept per env; more than that flags the env outright
 #define WF_STR_(x) #x
 #define WF_PRAGMA_UNROLL_(n) _Pragma(WF_STR_(unroll n))
 #ifndef WF_FAST_UNROLL_V
@@ -54,6 +55,13 @@ constexpr int kTurbPerPass = 10;
 #define WF_FAST_UNROLL_D 1
 #endif
 #define WF_UNROLL_D WF_PRAGMA_UNROLL_(WF_FAST_UNROLL_D)
+#ifndef WF_VTAB_PF_DIST
+#define WF_VTAB_PF_DIST 2  // the table rows of source i + WF_VTAB_PF_DIST are prefetched to L2 while source i is processed
+#endif
+#ifndef WF_FAST_UNROLL_T
+#define WF_FAST_UNROLL_T 2  // table passes in flight
+#endif
+#define WF_UNROLL_T WF_PRAGMA_UNROLL_(WF_FAST_UNROLL_T)
 #ifndef WF_FAST_MINB
 #define WF_FAST_MINB 12  // lower bound on resident env-CTAs per SM for the register allocator (16 are reached)
 #endif
@@ -63,6 +71,29 @@ __device__ __forceinline__ float fsqrt(float x) { float y; asm("sqrt.approx.ftz.
 __device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float flg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fclamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// Pull the vortex-table rows of sorted source `i` (contiguous: targets i+1 .. T-1) into L2 ahead of their use with ONE bulk
+// prefetch; the rows are read exactly once per step, so without this every pass of the V sweep would wait for HBM.
+template <int ROW_BYTES>
+__device__ __forceinline__ void prefetch_rows(const void* env_rows, int i, int T, int lane) {
+    if (i >= T - 1 || lane != 0) return;
+    const char* p = (const char*)env_rows + ((size_t)i * T - (size_t)i * (i + 1) / 2) * ROW_BYTES;
+    const unsigned bytes = (unsigned)(T - 1 - i) * ROW_BYTES;  // a multiple of 16, p is 16-byte aligned
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Table rows are read exactly once per step: fetch them with an evict-first L2 policy so that consumed lines make room for
+// the rows being prefetched instead of ageing through the LRU.
+__device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long pol) {
+    float4 v;
+#ifdef WF_VTAB_NO_EVICT_HINT
+    v = __ldg(p);
+#else
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+#endif
+    return v;
+}
 
 // piecewise-linear table lookup (np.interp + scipy fill values), warp-uniform or per-lane x
 __device__ __forceinline__ float interp_f(const WfFastConst& fc, const float* __restrict__ fp, float x, float left,
@@ -92,10 +123,13 @@ struct SmemView {
     unsigned char* ordr;      // [T]
     unsigned char* queue;     // [T] targets whose rotor can see source i's velocity deficit (compacted per source)
     float4* cblk;             // [12] per-model vortex constants, 4 float4 per vertical index k (LDS.128 broadcast)
+    float* evt_ta;            // [kMaxEvt] upper wake-added TI of an ambiguous overlap count (see the D sweep)
+    uchar2* evt_tj;           // [kMaxEvt] its (target, lateral column)
 };
 
 __host__ __device__ inline size_t fast_smem_bytes(int T) {
     size_t n = 12 * 16;          // cblk
+    n += (size_t)kMaxEvt * 4 + 16;  // evt_ta, evt_tj
     n += (size_t)3 * 9 * T * 4;  // wsq, v, w
     n += (size_t)2 * T * 8;      // xhl, yhl
     n += (size_t)3 * T * 4;      // tia
@@ -109,7 +143,9 @@ __host__ __device__ inline size_t fast_smem_bytes(int T) {
 __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
     SmemView s;
     s.cblk = (float4*)base;
-    float2* f2 = (float2*)(base + 12 * 16);
+    s.evt_ta = (float*)(base + 12 * 16);
+    s.evt_tj = (uchar2*)(base + 12 * 16 + kMaxEvt * 4);
+    float2* f2 = (float2*)(base + 12 * 16 + kMaxEvt * 4 + 16);
     s.xhl = f2;
     s.yhl = f2 + T;
     s.vw = f2 + 2 * T;  // 8-byte aligned for every T
@@ -130,8 +166,8 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int T) {
 struct wf_true_tag { static constexpr bool value = true; };
 struct wf_false_tag { static constexpr bool value = false; };
 
-template <bool BAKED>
-__global__ void __launch_bounds__(32, WF_FAST_MINB)
+template <bool BAKED, bool VTAB>
+__global__ void __launch_bounds__(32, VTAB ? 16 : WF_FAST_MINB)
 wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const __grid_constant__ WfFastConst fc,
                     const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
@@ -211,9 +247,26 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
     const float c_e = -KC(inv_eps2) * kLog2e;
     const float c_ek = -(0.5f * kLog2e) * (BAKED ? WfBaked::dz2_0 : fc.dz2[0]);
     const float eps2 = KC(eps2);
+    // Guard band of the ONE floating-point decision that makes the solve discontinuous: a rotor point counts towards the
+    // wake overlap when deficit * U0 > 0.05 m/s.  Counts are kept for both ends of the band; where they differ the event
+    // is recorded and judged when the target's turbulence intensity is final (see the source prologue).
+    const float thr_lo = 0.05f * (1.f - m.amb_eps), thr_hi = 0.05f * (1.f + m.amb_eps);
+    const double two_D_d = 2.0 * m.D;
+    int nevt = 0;
+    bool flagged = false;
+    // vortex table of this env (streamed front to back, one row per sorted pair i < t), or NULL: evaluate every pair directly
+    const float4* __restrict__ vrow = nullptr;
+    if (VTAB && s.vtab_ok[b]) vrow = (const float4*)s.vtab + (size_t)b * ((size_t)T * (T - 1) / 2) * 9;
+    unsigned long long pol_stream = 0;
+    if (VTAB) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    if (VTAB && vrow) {
+#pragma unroll
+        for (int d = 0; d < WF_VTAB_PF_DIST; ++d) prefetch_rows<144>(vrow, d, T, lane);
+    }
 
     // ---- sequential solver over sources -------------------------------------------------------------
     for (int i = 0; i < T; ++i) {
+        if (VTAB && vrow) prefetch_rows<144>(vrow, i + WF_VTAB_PF_DIST, T, lane);
         // ===== source prologue =====
         // rotor sums over the source's 9 points: one point per lane, butterfly over 16-lane halves -> uniform values
         float su3, sv, sw, vq, wwq;
@@ -264,6 +317,12 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         const float A_ln = (1.6f + sM0) * frcp(1.6f - sM0);
         const float inv_s0d = frcp(sy0d * sz0d);
 
+        // This turbine's wake-added TI is final now (all its sources are upstream).  An ambiguous overlap count is harmless
+        // when even its upper value stays below the running maximum; otherwise the env is flagged for the FP64 re-solve.
+        for (int e = 0; e < min(nevt, kMaxEvt); ++e) {
+            const uchar2 tj = sm.evt_tj[e];
+            if ((int)tj.x == i && sm.evt_ta[e] > sm.tia[3 * i + tj.y]) flagged = true;
+        }
         // TI of the source per lateral column before the yaw-added-recovery update
         const float ta0 = sm.tia[3 * i], ta1 = sm.tia[3 * i + 1], ta2 = sm.tia[3 * i + 2];
         const float tp0 = fsqrt(fmaf(ta0, ta0, I02)), tp1 = fsqrt(fmaf(ta1, ta1, I02)), tp2 = fsqrt(fmaf(ta2, ta2, I02));
@@ -325,12 +384,13 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         // A source at exactly zero yaw sheds no tip vortices (Gt = Gb = 0): the sweep then evaluates the wake-rotation
         // pair only -- same bits, 45 % of the work.  Warp-uniform choice, one instantiation of the loop per case.
         int qn = 0;
-        auto v_sweep = [&](auto yawed_tag) {
-        constexpr bool YAWED = decltype(yawed_tag)::value;
-        WF_UNROLL_V
-        for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
+        // with the table only the x-ties of the source (targets within 1e-6 m in x; none for a generic wind direction) take
+        // the direct path
+        const int t_hi = vrow ? (int)s.tab_lo[row + i] : T;
+        auto v_pass = [&](auto yawed_tag, const int t0) {
+            constexpr bool YAWED = decltype(yawed_tag)::value;
             const int tr = t0 + g;
-            const bool active = lane_ok && tr < T && tr != i;
+            const bool active = lane_ok && tr < t_hi && tr != i;
             const int t = min(tr, T - 1);  // inactive lanes compute on a valid turbine; only their stores are masked
             const float2 xt = sm.xhl[t], yt = sm.yhl[t];
             const float dx = (xt.x - xi.x) + (xt.y - xi.y);
@@ -388,9 +448,49 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
                     sm.vw[qb + k] = make_float2(o.x + Vk[k], o.y + Wk[k]);
                 }
             }
-        }
         };
-        if (sy != 0.f) v_sweep(wf_true_tag{}); else v_sweep(wf_false_tag{});
+        if (VTAB) {  // only x-ties come here (lo == i and t_hi == i + 1 without ties): one rolled, generic copy of the pass
+            if (t_hi - lo > 1) {
+#pragma unroll 1
+                for (int t0 = lo; t0 < t_hi; t0 += kTurbPerPass) v_pass(wf_true_tag{}, t0);
+            }
+        } else if (sy != 0.f) {
+            WF_UNROLL_V
+            for (int t0 = lo; t0 < t_hi; t0 += kTurbPerPass) v_pass(wf_true_tag{}, t0);
+        } else {
+            WF_UNROLL_V
+            for (int t0 = lo; t0 < t_hi; t0 += kTurbPerPass) v_pass(wf_false_tag{}, t0);
+        }
+        if (VTAB && vrow) {
+            // ===== V sweep through the table: V += Gt*cVt + Gwr*cVw ; W += max(Gt*cWt + Gwr*cWw, 0) per rotor point; a lane
+            //       reads the 48 contiguous bytes of its (target, column): a pass is one 1440-byte segment of the stream =====
+            const float4* __restrict__ src = vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 9 + 3 * j;
+            WF_UNROLL_T
+            for (int t0 = t_hi; t0 < T; t0 += kTurbPerPass) {
+                const int tr = t0 + g;
+                const bool active = lane_ok && tr < T;
+                const int t = min(tr, T - 1);
+                const float4* __restrict__ rp = src + (size_t)(t - i - 1) * 9;
+                const float4 c0 = ldg_stream(rp, pol_stream), c1 = ldg_stream(rp + 1, pol_stream), c2 = ldg_stream(rp + 2, pol_stream);
+                const float2 xt = sm.xhl[t], yt = sm.yhl[t];
+                const float dx = (xt.x - xi.x) + (xt.y - xi.y);
+                const float dyc = ((yt.x - yi.x) + (yt.y - yi.y)) + offj;
+                const bool need = active && (t >= near_i) &&
+                                  (fabsf(dyc) < fmaf(reach1, dx, reach0) + fabsf(fmaf(KC(bd), dx, KC(ad))));
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
+                const unsigned lb = __ballot_sync(0xffffffffu, leader);
+                if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
+                qn += __popc(lb);
+                if (active) {
+                    const int qb = 9 * t + 3 * j;
+                    const float2 o0 = sm.vw[qb], o1 = sm.vw[qb + 1], o2 = sm.vw[qb + 2];
+                    sm.vw[qb] = make_float2(o0.x + fmaf(Gt, c0.x, Gwr * c0.y), o0.y + fmaxf(fmaf(Gt, c0.z, Gwr * c0.w), 0.f));
+                    sm.vw[qb + 1] = make_float2(o1.x + fmaf(Gt, c1.x, Gwr * c1.y), o1.y + fmaxf(fmaf(Gt, c1.z, Gwr * c1.w), 0.f));
+                    sm.vw[qb + 2] = make_float2(o2.x + fmaf(Gt, c2.x, Gwr * c2.y), o2.y + fmaxf(fmaf(Gt, c2.z, Gwr * c2.w), 0.f));
+                }
+            }
+        }
         __syncwarp();
 
         // ===== D sweep: deflection + Gaussian deficit + wake-added TI, only on the queued targets =====
@@ -432,9 +532,10 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
             }
             const float be = base * ek;
             const float dU0 = be * U0a, dU1 = base * U0b, dU2 = be * U0c;
-            int c = 0;
+            int c = 0;  // points over the threshold: low byte with the upper end of the guard band, next byte with the lower
             if (active) {
-                c = (dU0 > 0.05f) + (dU1 > 0.05f) + (dU2 > 0.05f);
+                c = ((dU0 > thr_hi) + (dU1 > thr_hi) + (dU2 > thr_hi)) |
+                    (((dU0 > thr_lo) + (dU1 > thr_lo) + (dU2 > thr_lo)) << 8);
                 const int qb = 9 * t + 3 * j;
                 sm.wsq[qb] = fmaf(dU0, dU0, sm.wsq[qb]);
                 sm.wsq[qb + 1] = fmaf(dU1, dU1, sm.wsq[qb + 1]);
@@ -444,10 +545,32 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
             const int gb = 3 * g;
             const int c_tot = __shfl_sync(0xffffffffu, c, gb & 31) + __shfl_sync(0xffffffffu, c, (gb + 1) & 31) +
                               __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
-            if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabsf(dyc) < KC(two_D)) {
-                const float wat = watK * __powf(dx * KC(inv_D), KC(ch_down));
-                const float ta = (float)c_tot * (1.f / 9.f) * wat;
-                sm.tia[3 * t + j] = fmaxf(sm.tia[3 * t + j], ta);
+            const int c_lo = c_tot & 0xff, c_hi = c_tot >> 8;
+            bool ambiguous = false;
+            float ta_hi = 0.f;
+            if (active && c_hi > 0 && t >= gt0_i && t < end15) {
+                const float ady = fabsf(dyc);
+                bool in_win = ady < KC(two_D);
+                if (fabsf(ady - KC(two_D)) < 2e-3f) {  // lateral window |Y - y_i| < 2 D decided on the float-float positions
+                    const double d = (((double)yt.x - (double)yi.x) + ((double)yt.y - (double)yi.y)) + (double)offj;
+                    in_win = fabs(d) < two_D_d;
+                    if (fabs(fabs(d) - two_D_d) < 1e-7) flagged = true;
+                }
+                if (in_win) {
+                    const float wat = watK * __powf(dx * KC(inv_D), KC(ch_down));
+                    if (c_lo > 0) sm.tia[3 * t + j] = fmaxf(sm.tia[3 * t + j], (float)c_lo * (1.f / 9.f) * wat);
+                    ambiguous = c_hi != c_lo;
+                    ta_hi = (float)c_hi * (1.f / 9.f) * wat;
+                }
+            }
+            const unsigned ab = __ballot_sync(0xffffffffu, ambiguous);
+            if (ab) {  // rare
+                const int slot = nevt + __popc(ab & ((1u << lane) - 1u));
+                if (ambiguous) {
+                    if (slot < kMaxEvt) { sm.evt_ta[slot] = ta_hi; sm.evt_tj[slot] = make_uchar2((unsigned char)t, (unsigned char)j); }
+                    else flagged = true;
+                }
+                nevt += __popc(ab);
             }
         }
         __syncwarp();
@@ -516,7 +639,9 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         rsum_p += __shfl_xor_sync(0xffffffffu, rsum_p, sft);
         rsum_l += __shfl_xor_sync(0xffffffffu, rsum_l, sft);
     }
+    const bool any_flag = __any_sync(0xffffffffu, flagged);
     if (lane == 0) {
+        if (s.amb) s.amb[b] = (uint8_t)any_flag;
         const int it = s.num_iter[b] + 1;
         s.num_iter[b] = it;
         if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
@@ -545,7 +670,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
 
 }  // namespace
 
-template <bool BAKED>
+template <bool BAKED, bool VTAB>
 static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                  const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                  const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
@@ -554,39 +679,43 @@ static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& 
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED, VTAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED, VTAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     static const size_t pad = getenv("WFCRL_SMEM_PAD") ? (size_t)atoi(getenv("WFCRL_SMEM_PAD")) : 0;  // tuning experiments
-    wf_step_fast_kernel<BAKED><<<env_count, 32, smem + pad, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    wf_step_fast_kernel<BAKED, VTAB><<<env_count, 32, smem + pad, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_step_fast(int mode, bool baked, const WfModel& m, const WfFastConst& fc, const WfState& s,
+cudaError_t wf_launch_step_fast(int mode, bool baked, bool use_vtab, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                 const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
-    return baked ? launch_fast_t<true>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream)
-                 : launch_fast_t<false>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream);
+#define WF_GO(B_, V_) launch_fast_t<B_, V_>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream)
+    const bool vtab = use_vtab && s.vtab != nullptr;
+    return baked ? (vtab ? WF_GO(true, true) : WF_GO(true, false)) : (vtab ? WF_GO(false, true) : WF_GO(false, false));
+#undef WF_GO
 }
 
-template <bool BAKED>
+template <bool BAKED, bool VTAB>
 static cudaError_t attrs_fast_t(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads, int* smem) {
     *threads = 32;
     *smem = (int)fast_smem_bytes(m.T);
-    cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaError_t e = cudaFuncSetAttribute(wf_step_fast_kernel<BAKED, VTAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(attr, wf_step_fast_kernel<BAKED>);
+    e = cudaFuncGetAttributes(attr, wf_step_fast_kernel<BAKED, VTAB>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast_kernel<BAKED>, 32, *smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast_kernel<BAKED, VTAB>, 32, *smem);
 }
 
-cudaError_t wf_step_fast_attributes(bool baked, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm,
+cudaError_t wf_step_fast_attributes(bool baked, bool use_vtab, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm,
                                     int* threads, int* smem) {
-    return baked ? attrs_fast_t<true>(m, attr, ctas_per_sm, threads, smem)
-                 : attrs_fast_t<false>(m, attr, ctas_per_sm, threads, smem);
+    if (use_vtab) return baked ? attrs_fast_t<true, true>(m, attr, ctas_per_sm, threads, smem)
+                               : attrs_fast_t<false, true>(m, attr, ctas_per_sm, threads, smem);
+    return baked ? attrs_fast_t<true, false>(m, attr, ctas_per_sm, threads, smem)
+                 : attrs_fast_t<false, false>(m, attr, ctas_per_sm, threads, smem);
 }

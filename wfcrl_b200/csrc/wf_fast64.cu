@@ -26,6 +26,14 @@ constexpr double kRad = kPi / 180.0;
 constexpr double kNumEps = 0.001;
 constexpr int kTurbPerPass = 10;
 
+// see wf_fast.cu: pull the vortex-table rows of sorted source `i` into L2 ahead of their use (one bulk prefetch)
+__device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int T, int lane) {
+    if (i >= T - 1 || lane != 0) return;
+    const char* p = (const char*)env_rows + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 288;
+    const unsigned bytes = (unsigned)(T - 1 - i) * 288;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ double dclamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double* __restrict__ fp, double x, double left,
@@ -91,7 +99,7 @@ __device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T) {
 }
 
 __global__ void __launch_bounds__(32, 4)
-wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, const __grid_constant__ WfFastConst64 fc,
+wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
                       const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                       const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
     const int b = blockIdx.x + env_begin;
@@ -165,8 +173,13 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
     const double cwl0 = fc.cw[0][plc], cwl1 = fc.cw[1][plc], cwl2 = fc.cw[2][plc];
     const double c_dec = fc.eps2 * fc.inv_2pi;
     const double eps2 = fc.eps2;
+    // vortex table of this env (wf_device.cuh), or NULL: evaluate every pair directly
+    const double2* __restrict__ vrow = nullptr;
+    if (use_vtab && s.vtab && s.vtab_ok[b]) vrow = (const double2*)s.vtab + (size_t)b * ((size_t)T * (T - 1) / 2) * 18;
+    if (vrow) { prefetch_rows64(vrow, 0, T, lane); prefetch_rows64(vrow, 1, T, lane); }
 
     for (int i = 0; i < T; ++i) {
+        if (vrow) prefetch_rows64(vrow, i + 2, T, lane);
         // ===== source prologue =====
         double su3, sv, sw, vq, wwq;
         {
@@ -269,9 +282,11 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
 
         // ===== V sweep =====
         int qn = 0;
-        for (int t0 = lo; t0 < T; t0 += kTurbPerPass) {
+        const int t_hi = vrow ? (int)s.tab_lo[row + i] : T;  // with the table only the x-ties take the direct path
+#pragma unroll 1
+        for (int t0 = lo; t0 < ((t_hi - lo > 1 || !vrow) ? t_hi : lo); t0 += kTurbPerPass) {  // without ties [lo, t_hi) = {i}
             const int tr = t0 + g;
-            const bool active = lane_ok && tr < T && tr != i;
+            const bool active = lane_ok && tr < t_hi && tr != i;
             const int t = min(tr, T - 1);
             const double dx = sm.xs[t] - x_i;
             const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
@@ -314,6 +329,38 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
                 for (int k = 0; k < 3; ++k) {
                     const double2 o = sm.vw[qb + k];
                     sm.vw[qb + k] = make_double2(o.x + Vk[k], o.y + Wk[k]);
+                }
+            }
+        }
+        if (vrow) {
+            // V sweep through the table: V += Gt*cVt + Gwr*cVw ; W += max(Gt*cWt + Gwr*cWw, 0); a lane streams the 96
+            // contiguous bytes of its (target, column)
+            const double2* __restrict__ src = vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 18 + 6 * j;
+#pragma unroll 2
+            for (int t0 = t_hi; t0 < T; t0 += kTurbPerPass) {
+                const int tr = t0 + g;
+                const bool active = lane_ok && tr < T;
+                const int t = min(tr, T - 1);
+                const double2* __restrict__ rp = src + (size_t)(t - i - 1) * 18;
+                double2 c[6];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) c[e] = __ldg(rp + e);
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                const bool need = active && (t >= near_i) && (fabs(dyc) < reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad));
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
+                const unsigned lb = __ballot_sync(0xffffffffu, leader);
+                if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
+                qn += __popc(lb);
+                if (active) {
+                    const int qb = 9 * t + 3 * j;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double2 o = sm.vw[qb + k];
+                        sm.vw[qb + k] = make_double2(o.x + (Gt * c[2 * k].x + Gwr * c[2 * k].y),
+                                                     o.y + fmax(Gt * c[2 * k + 1].x + Gwr * c[2 * k + 1].y, 0.0));
+                    }
                 }
             }
         }
@@ -474,7 +521,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const WfModel m, cons
 
 }  // namespace
 
-cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                   const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
     const size_t smem = fast64_smem_bytes(m.T);
@@ -489,7 +536,7 @@ cudaError_t wf_launch_step_fast64(int mode, const WfModel& m, const WfFastConst6
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    wf_step_fast64_kernel<<<env_count, 32, smem, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    wf_step_fast64_kernel<<<env_count, 32, smem, stream>>>(mode, env_begin, use_vtab, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 

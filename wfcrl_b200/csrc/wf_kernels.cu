@@ -217,16 +217,84 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
         const size_t o = (size_t)b * T + t;
         const double x_i = s.xi[o];
         const double x01 = __dadd_rn(x_i, 0.1), x15 = __dadd_rn(15 * m.D, x_i);
-        int i0 = T, i1 = T, i2 = T, i3 = T;
+        const double xtie = __dadd_rn(xsrt[t], 1e-6);
+        int i0 = T, i1 = T, i2 = T, i3 = T, i4 = T;
         for (int q = T - 1; q >= 0; --q) {
             const double xq = xsrt[q];
             if (__dsub_rn(xq, x_i) >= 0.0) i0 = q;
             if (xq > x01) i1 = q;
             if (xq > x_i) i2 = q;
             if (xq > x15) i3 = q;
+            if (xq > xtie) i4 = q;
         }
         s.idx[o] = make_uchar4((unsigned char)i0, (unsigned char)i1, (unsigned char)i2, (unsigned char)i3);
+        s.tab_lo[o] = (unsigned char)i4;
     }
+    if (t == 0 && s.vtab_ok) s.vtab_ok[b] = 0;  // the vortex table of this env no longer matches its geometry
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// vortex table: geometry-only coefficients of the transverse velocities, one row per sorted pair i < t.
+// Evaluated in FP64 with the accurate math functions whatever the handle's precision; stored as R.
+// One CTA per env; a thread owns one (row, lateral column) and writes its 12 coefficients [k][cVt, cVw, cWt, cWw].
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256)
+wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc, const WfState s,
+                       const uint8_t* __restrict__ mask) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int T = m.T;
+    __shared__ double xs[WF_MAX_TURBINES_K], ys[WF_MAX_TURBINES_K], xi[WF_MAX_TURBINES_K], yi[WF_MAX_TURBINES_K];
+    __shared__ int rowoff[WF_MAX_TURBINES_K];
+    const size_t row0 = (size_t)b * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        xs[t] = s.xs[row0 + t];
+        ys[t] = s.ys[row0 + t];
+        xi[t] = s.xi[row0 + t];
+        yi[t] = s.yi[row0 + t];
+        rowoff[t] = t * T - t * (t + 1) / 2;
+    }
+    __syncthreads();
+    const int rows = T * (T - 1) / 2;
+    R* __restrict__ tab = (R*)s.vtab + (size_t)b * rows * 36;
+    const double rho = fc.c_bot / fc.c_top;  // Gb = -rho * Gt
+    const double c_dec = fc.eps2 * fc.inv_2pi;
+    for (int task = threadIdx.x; task < rows * 3; task += blockDim.x) {
+        const int row = task / 3, j = task - 3 * row;
+        // row -> (i, t): largest i with rowoff[i] <= row
+        int lo = 0, hi = T - 2;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rowoff[mid] <= row) lo = mid; else hi = mid - 1;
+        }
+        const int i = lo, t = i + 1 + (row - rowoff[i]);
+        const double dx = xs[t] - xi[i];
+        const double dyc = __dsub_rn(__dadd_rn(ys[t], fc.offj[j]), yi[i]);
+        const double yL = dyc + kNumEps;
+        const double q = yL * yL;
+        const double E = exp(-q * fc.inv_eps2);
+        R* dst = tab + (size_t)row * 36 + j * 12;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double A[3], Bc[3];  // per unit circulation of (top pair, bottom pair, wake-rotation pair): V and W sums
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+                const int va = (pr == 0) ? 0 : (pr == 1 ? 1 : 4), vb = (pr == 0) ? 2 : (pr == 1 ? 3 : 5);  // real, ground mirror
+                const double ra = q + fc.zz2[va][k], rb = q + fc.zz2[vb][k];
+                const double fa = (1.0 - E * fc.ez[va][k]) / ra, fb = (1.0 - E * fc.ez[vb][k]) / rb;
+                A[pr] = fc.zz[va][k] * fa - fc.zz[vb][k] * fb;
+                Bc[pr] = fa - fb;
+            }
+            const double dec = c_dec / (fc.nu4[k] * dx + fc.eps2);
+            dst[4 * k + 0] = (R)(dec * (A[0] - rho * A[1]));
+            dst[4 * k + 1] = (R)(dec * A[2]);
+            dst[4 * k + 2] = (R)(-yL * dec * (Bc[0] - rho * Bc[1]));
+            dst[4 * k + 3] = (R)(-yL * dec * Bc[2]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s.vtab_ok[b] = 1;  // read by later launches on the same stream only
 }
 
 // FlorisInterface.update_wind for masked envs: new free-stream wind, counters untouched (interface.py:663-671)
@@ -732,6 +800,14 @@ static inline int round_up_warp(int n) { return (n + 31) / 32 * 32; }
 cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_cs_override,
                                cudaStream_t stream) {
     wf_geometry_kernel<<<m.B, round_up_warp(m.T), 0, stream>>>(m, s, d_mask, d_cs_override);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_vortex_table(int precision, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                                   const uint8_t* d_mask, cudaStream_t stream) {
+    if (!s.vtab || m.T < 2) return cudaSuccess;
+    if (precision == 0) wf_vortex_table_kernel<double><<<m.B, 256, 0, stream>>>(m, fc, s, d_mask);
+    else wf_vortex_table_kernel<float><<<m.B, 256, 0, stream>>>(m, fc, s, d_mask);
     return cudaGetLastError();
 }
 
