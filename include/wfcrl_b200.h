@@ -11,7 +11,8 @@
  *  - plain pointers and sizes only; no C++/torch types; every function returns WF_OK (0) or an error code and
  *    never throws; `wf_last_error()` returns a thread-local human-readable message.
  *  - "real" = double when the handle was created with WF_PREC_F64 (bit-check mode, <=1e-9 relative vs the
- *    reference arithmetic) and float with WF_PREC_F32 (fast mode, <=1e-4 relative).
+ *    reference arithmetic) and float with WF_PREC_F32 (fast mode, <=1e-4 relative on every turbine with the tuned
+ *    kernel unless WfConfig.fp32_relaxed is set).
  *  - all `d_*` pointers are DEVICE pointers on the handle's device, all `h_*` pointers are HOST pointers.
  *  - per-turbine arrays are row-major [num_envs][num_turbines] in the ORIGINAL turbine order of the layout.
  *  - output buffers must be aligned to 16 bytes (`load` is written with 128-bit stores, `freewind` with 64-bit stores).
@@ -58,10 +59,15 @@ typedef struct WfConfig {
     int32_t continuous_control; /* mdp.py:300-310: 1 = Box actions clipped to +-step, 0 = {0,1,2} -> (a-1)*step */
     int32_t multi_agent;        /* 1 = actuation constraint with the per-agent staleness of multiagent_env.py:198-249 */
     int32_t reward_shaper;      /* enum WfShaper */
-    int32_t reserved0;
+    int32_t fp32_relaxed;       /* WF_PREC_F32 + WF_KERNEL_FAST only.  0 (default) = strict: solves whose discrete decisions (wake
+                                   overlap count, 2D window) or power-curve conditioning are beyond FP32 are detected in the
+                                   step kernel and redone by the FP64 kernel in a second launch, so that every turbine meets
+                                   the 1e-4 tolerance; 1 = raw FP32 results, no second launch (a few envs in 1e4 differ by up
+                                   to ~1e-2) */
     double yaw_lo, yaw_hi, yaw_step; /* controls["yaw"] = (low, high, step), default (-40, 40, 5) */
     double load_coef;                /* simple_env.py:25 */
-    double shaper_reference;         /* ReferencePercentage.reference / StepPercentage initial reference */
+    double shaper_reference;         /* ReferencePercentage.reference (StepPercentage always restarts from 0 at reset,
+                                        rewards.py:45-46, whatever its constructor argument) */
     double dt;                       /* FlorisCase.dt = 60 (data_cases.py:507) */
     double actuator_rate;            /* mdp.py:52 ACTUATORS_RATE["yaw"] = 0.3 */
     /* flow field (case.yaml:30-39) */
@@ -195,6 +201,7 @@ int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);
  *   "yaw" f64[B][T] | "acc" f32[B][T] | "acc_prev" f32[B][T] | "num_iter" i32[B] | "num_moves" i32[B] |
  *   "nonfinite" i32[B] (guard counter: env steps whose reward was NaN/Inf since creation) |
  *   "episode" i32[B] (sampled resets so far: the counter word of wf_reset_sampled) |
+ *   "ambiguous" u8[B] (strict FP32 handles: 1 = the last solve of this env was redone in FP64) |
  *   "ws" f64[B] | "wd" f64[B] | "ws_norm" f64[B] | "shaper_ref" f64[B] | "ti_ambient" f64[B] |
  *   "order" i32[B][T] | "xs" f64[B][T] | "ys" f64[B][T] | "xi" f64[B][T] | "yi" f64[B][T] | "cs" f64[B][2]
  * `bytes` must equal the full array size.

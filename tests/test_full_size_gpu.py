@@ -36,22 +36,31 @@ def test_full_batch_against_oracle_subset_and_properties(cuda_device, name, B, p
     torch.cuda.synchronize()
     got = {k: v.double().cpu().numpy() for k, v in out.items()}
 
-    # (1) oracle on a random subset (C restatement, same rotation, yaw after the float32 transition)
-    sub = rng.choice(B, size=256, replace=False)
+    # (1) oracle on EVERY env of the batch (C restatement, same rotation, yaw after the float32 transition)
+    sub = np.arange(B)
     yaw1 = np.clip(np.clip(yaw0, -40, 40) + np.clip(act, -5, 5), -40, 40).astype(np.float32)
     assert np.array_equal(got["yaw"].astype(np.float32), yaw1)  # bit-exact float32 transition for the WHOLE batch
     c, s = host_trig(wd[sub])
     ref = c_oracle.solve_batch(lx, ly, ws[sub], wd[sub], yaw1[sub].astype(np.float64), cs=np.stack([c, s], 1))
     perr = np.abs(got["power"][sub] * 1e6 - ref["power_W"]) / np.maximum(ref["power_W"], 1.0)
     tol = 1e-9 if precision == "f64" else 1e-4
-    # FP32: allow a vanishing fraction of threshold flips of the wake-overlap count
-    frac_bad = np.mean(perr > tol)
-    assert frac_bad <= (0.0 if precision == "f64" else 2e-3), (frac_bad, perr.max())
+    # every turbine of every env, no allowance: the FP32 kernel hands the solves it cannot decide (wake-overlap threshold,
+    # foot of the power curve) to the FP64 kernel; floor of 1 W on a 5 MW turbine
+    assert perr.max() <= tol, (np.mean(perr > tol), perr.max())
     assert np.median(perr) < (1e-12 if precision == "f64" else 2e-6)
+    if precision == "f32" and kernel == "fast":
+        n_fix = int(fb.get_state("ambiguous").sum())
+        assert n_fix <= max(8, B // 20), n_fix  # the FP64 re-solve stays the exception
     loads = np.stack([ref["ti"], ref["std_u"], ref["std_v"], ref["std_w"]], -1)
     reward = np.mean(ref["power_W"] / 1e6 * 1e3 / np.clip(ws[sub], 3, 28)[:, None] ** 3, 1) - 0.1 * np.mean(np.abs(loads), (1, 2))
     rerr = np.abs(got["reward"][sub] - reward) / np.abs(reward)
-    assert np.mean(rerr > tol) <= (0.0 if precision == "f64" else 2e-3) and np.median(rerr) < (1e-12 if precision == "f64" else 2e-6)
+    assert rerr.max() <= tol and np.median(rerr) < (1e-12 if precision == "f64" else 2e-6)
+    # local wind speed and load proxies of the whole batch.  FP32 loads: 2e-4 relative with an absolute floor of 5e-6
+    # (std of v / w are ~1e-3..1e-1 m/s sums of differences of O(10) m/s values: their error is absolute, ~1e-6 m/s)
+    wsl_err = np.abs(got["wind_speed"] - ref["ws_local"]) / ref["ws_local"]
+    assert wsl_err.max() <= (1e-9 if precision == "f64" else 3e-5), wsl_err.max()
+    lerr = np.abs(got["load"] - loads)
+    assert np.all(lerr <= ((1e-9 * np.abs(loads) + 1e-13) if precision == "f64" else (2e-4 * np.abs(loads) + 5e-6))), lerr.max()
     assert np.array_equal(fb.get_state("order")[sub], ref["order"])
 
     # (2) determinism: same state + action -> bitwise identical outputs

@@ -48,9 +48,14 @@ def test_solve_matches_oracle(cuda_device, name, precision, kernel):
     assert rel_err(got["wind_speed"], ref["ws_local"], 1e-3) <= tol
     assert rel_err(got["wind_direction"], ref["wd_local"], 1.0) <= tol
     loads_ref = np.stack([ref["ti"], ref["std_u"], ref["std_v"], ref["std_w"]], -1) * 1e7
-    # std of v / w can be ~1e-3 m/s; compare loads relative to a floor of 1e-3 (x1e7)
-    ltol = tol if precision == "f64" else 2e-3
-    assert rel_err(got["load"], loads_ref, 1e4) <= ltol
+    # FP32 loads: 2e-4 relative plus an absolute 5e-6 (x1e7): std of v / w are small differences of O(10) m/s values, so
+    # their error is absolute (~1e-6 m/s); the basic FP32 kernel (plain transcription, not the product path) keeps 2e-3
+    if precision == "f64":
+        assert rel_err(got["load"], loads_ref, 1e4) <= tol
+    elif kernel == "fast":
+        assert np.all(np.abs(got["load"] - loads_ref) <= 2e-4 * np.abs(loads_ref) + 50.0)
+    else:
+        assert rel_err(got["load"], loads_ref, 1e4) <= 2e-3
     assert np.allclose(got["freewind"][:, 0], ws) and np.allclose(got["freewind"][:, 1], wd)
 
 

@@ -14,8 +14,9 @@ def _solve(name, precision, B, seed, monkeypatch, table):
 
     from wfcrl_b200.backend import FlorisBatch
 
-    if table:
+    if table:  # FP64 handles build the table by default, FP32 handles on request
         monkeypatch.delenv("WFCRL_B200_NO_VTAB", raising=False)
+        monkeypatch.setenv("WFCRL_B200_VTAB", "1")
     else:
         monkeypatch.setenv("WFCRL_B200_NO_VTAB", "1")
     lx, ly = layout(name)

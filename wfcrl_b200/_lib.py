@@ -21,7 +21,7 @@ class WfConfig(C.Structure):
     _fields_ = [
         ("num_turbines", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32),
         ("kernel", C.c_int32), ("max_iter", C.c_int32), ("continuous_control", C.c_int32),
-        ("multi_agent", C.c_int32), ("reward_shaper", C.c_int32), ("reserved0", C.c_int32),
+        ("multi_agent", C.c_int32), ("reward_shaper", C.c_int32), ("fp32_relaxed", C.c_int32),
         ("yaw_lo", C.c_double), ("yaw_hi", C.c_double), ("yaw_step", C.c_double),
         ("load_coef", C.c_double), ("shaper_reference", C.c_double), ("dt", C.c_double),
         ("actuator_rate", C.c_double),

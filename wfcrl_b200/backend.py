@@ -44,7 +44,7 @@ class FlorisBatch:
                  precision: str = "f64", kernel: str = "basic", max_iter: int = 500,
                  yaw_bounds=(-40.0, 40.0, 5.0), load_coef: float = 0.1, reward_shaper: str = "none",
                  shaper_reference: float = 0.0, continuous_control: bool = True, multi_agent: bool = False,
-                 config_overrides: Optional[Dict[str, float]] = None):
+                 strict: bool = True, config_overrides: Optional[Dict[str, float]] = None):
         if not torch.cuda.is_available():
             raise _lib.WfError("wfcrl_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
@@ -59,6 +59,7 @@ class FlorisBatch:
         cfg.max_iter = int(max_iter)
         cfg.continuous_control = int(bool(continuous_control))
         cfg.multi_agent = int(bool(multi_agent))
+        cfg.fp32_relaxed = int(not strict)  # FP32 fast kernel only: skip the guard band + FP64 re-solve (raw FP32 results)
         cfg.reward_shaper = _SHAPER[reward_shaper]
         cfg.shaper_reference = float(shaper_reference)
         cfg.yaw_lo, cfg.yaw_hi, cfg.yaw_step = (float(v) for v in yaw_bounds)

@@ -51,6 +51,11 @@ struct WfHandle_t {
     static constexpr int kHostStreams = 6;
     cudaStream_t host_streams[kHostStreams] = {};  // one per chunk of the wf_step_host pipeline
     uint64_t launches = 0;
+    // ordering of the host-buffer entry points (which run on the handle's own streams) after asynchronous calls the caller
+    // queued on ITS stream: those record this event, wf_step_host / wf_update_command_host make their streams wait on it
+    cudaEvent_t ev_async = nullptr;
+    bool ev_pending = false;
+    bool fast_uses_vtab = false;  // FP32 step kernel reads the vortex table (off by default: measured slower than direct)
     bool vtab_stale = false;  // some env's vortex-table rows do not match its geometry: launch the kernels that ignore the table
     uint64_t steps_since_wind_update = 1u << 30;  // wf_update_wind rebuilds the vortex table only when it is not called every step
 };
@@ -71,16 +76,23 @@ template <typename T> static int dev_alloc(WfHandle_t* h, T** p, size_t n) {
         if (_r != WF_OK) return _r; \
     } while (0)
 
+// called at the end of every asynchronous entry point: later host-buffer calls must run after the work queued here
+static int mark_async(WfHandle h, cudaStream_t st) {
+    CUDA_TRY(cudaEventRecord(h->ev_async, st));
+    h->ev_pending = true;
+    return WF_OK;
+}
+
 // rotated + sorted geometry of the selected envs and, unless told otherwise, their vortex-table rows
 static cudaError_t launch_geometry(WfHandle h, const uint8_t* d_mask, const double* d_cs, cudaStream_t st,
                                    bool build_table = true) {
     cudaError_t e = wf_launch_geometry(h->model, h->st, d_mask, d_cs, st);
     h->launches += 1;
-    if (e == cudaSuccess && build_table && h->st.vtab) {
-        e = wf_launch_vortex_table(h->cfg.precision, h->model, h->fast64, h->st, d_mask, st);
+    if (e == cudaSuccess && build_table && h->st.vtab_ok) {
+        e = wf_launch_vortex_table(h->model, h->fast64, h->st, d_mask, st);
         h->launches += 1;
         if (!d_mask) h->vtab_stale = false;
-    } else if (h->st.vtab) {
+    } else if (h->st.vtab_ok) {
         h->vtab_stale = true;
     }
     return e;
@@ -108,6 +120,7 @@ int wf_destroy(WfHandle h) {
     if (h->h_rcs) cudaFreeHost(h->h_rcs);
     for (cudaStream_t st : h->host_streams)
         if (st) cudaStreamDestroy(st);
+    if (h->ev_async) cudaEventDestroy(h->ev_async);
     delete h;
     return WF_OK;
 }
@@ -157,6 +170,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     m.yaw_lo_f = (float)cfg->yaw_lo; m.yaw_hi_f = (float)cfg->yaw_hi; m.yaw_step_f = (float)cfg->yaw_step;
     m.rate_f = (float)cfg->actuator_rate; m.dt_f = (float)cfg->dt;
     m.amb_eps = getenv("WFCRL_B200_AMB_EPS") ? (float)atof(getenv("WFCRL_B200_AMB_EPS")) : kDefaultAmbEps;
+    if (cfg->fp32_relaxed) m.amb_eps = 0.f;  // no guard band, no FP64 re-solve: raw FP32 results
     m.load_coef = cfg->load_coef; m.shaper_reference = cfg->shaper_reference;
     m.rho = cfg->air_density; m.ref_rho = cfg->ref_density_cp_ct; m.shear = cfg->wind_shear;
     m.D = cfg->rotor_diameter; m.HH = cfg->hub_height; m.TSR = cfg->tsr; m.pP = cfg->pP;
@@ -200,6 +214,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
         (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) || (rc = dev_alloc(h, &s.amb, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)2 * WF_FIX_SLOTS)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -210,22 +225,36 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         (rc = dev_alloc(h, &h->d_rcs, (size_t)2 * B)))
         return fail(rc);
     if ((rc = dev_alloc(h, &s.tab_lo, BT))) return fail(rc);
+    // The vortex table trades the V sweep's arithmetic for one streamed read of 36 reals per turbine pair.  Measured on B200
+    // (profiles/r2_vortex_table.md): it pays in the FP64 kernels (whose sweep is 3x more expensive), but not in the FP32 kernel,
+    // where the instructions that remain are latency-bound and the direct evaluation wins by 6 % -- so an FP32 handle builds
+    // float rows for its own kernel only when WFCRL_B200_VTAB=1 asks for it.  A strict FP32 handle builds DOUBLE rows for its
+    // FP64 re-solve kernel, which reads those of the few flagged envs (float rows would cost it 1e-9 of the rotor speed, too
+    // much at the foot of the power curve).  WFCRL_B200_NO_VTAB=1 disables every table; tables that would not fit
+    // comfortably are skipped and the kernels evaluate every pair directly.
     if (cfg->kernel == WF_KERNEL_FAST && T >= 2 && !getenv("WFCRL_B200_NO_VTAB")) {
-        // vortex table (wf_device.cuh): 36 reals per sorted turbine pair and env; skipped when it would not fit comfortably
-        const size_t bytes = (size_t)B * ((size_t)T * (T - 1) / 2) * 36 * h->es;
+        const size_t rows_all = (size_t)B * ((size_t)T * (T - 1) / 2) * 36;
         const size_t cap = (size_t)(getenv("WFCRL_B200_VTAB_MAX_MB") ? atof(getenv("WFCRL_B200_VTAB_MAX_MB")) : 24576.0) << 20;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (bytes <= cap && bytes <= free_b / 2) {
+        auto try_alloc = [&](size_t bytes) -> void* {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (bytes > cap || bytes > free_b / 2) return nullptr;
             void* p = nullptr;
-            if (cudaMalloc(&p, bytes) == cudaSuccess) {
-                h->allocs.push_back(p);
-                s.vtab = p;
-                if ((rc = dev_alloc(h, &s.vtab_ok, (size_t)B))) return fail(rc);
-            } else {
-                cudaGetLastError();
-            }
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            h->allocs.push_back(p);
+            return p;
+        };
+        const bool vtab_in_main = getenv("WFCRL_B200_VTAB") && atoi(getenv("WFCRL_B200_VTAB")) != 0;
+        if (cfg->precision == WF_PREC_F64) {
+            s.vtab64 = (double*)try_alloc(rows_all * 8);
+            s.vtab = s.vtab64;
+        } else {
+            if (m.amb_eps > 0.f) s.vtab64 = (double*)try_alloc(rows_all * 8);
+            if (vtab_in_main) s.vtab = try_alloc(rows_all * 4);
+            h->fast_uses_vtab = s.vtab != nullptr;
         }
+        if (s.vtab || s.vtab64)
+            if ((rc = dev_alloc(h, &s.vtab_ok, (size_t)B))) return fail(rc);
     }
     if (cudaMallocHost((void**)&h->h_mask, B) != cudaSuccess || cudaMallocHost((void**)&h->h_rws, sizeof(double) * B) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_rwd, sizeof(double) * B) != cudaSuccess ||
@@ -234,6 +263,8 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     for (cudaStream_t& st : h->host_streams)
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
             return fail(set_err(WF_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreateWithFlags(&h->ev_async, cudaEventDisableTiming) != cudaSuccess)
+        return fail(set_err(WF_ERR_CUDA, "cudaEventCreate failed"));
 
     // initial condition: wind (8, 270) as in FlorisCase.simul_params (data_cases.py:99-100), ambient TI from the config
     {
@@ -263,14 +294,21 @@ static WfOutPtrs to_ptrs(const WfStepOut* o) {
 }
 
 static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float* d_action, const double* d_yaw,
-                       const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1) {
+                       const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1,
+                       int slot = WF_FIX_SLOTS - 1) {
     if (env_count < 0) env_count = h->model.B;
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64)
         e = wf_launch_step_fast64(mode, !h->vtab_stale, h->model, h->fast64, h->st, d_mask, d_action, d_yaw, out, env_begin, env_count, st);
     else if (h->cfg.kernel == WF_KERNEL_FAST)
-        e = wf_launch_step_fast(mode, h->fast_baked, !h->vtab_stale, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
-                                env_count, st);
+    {
+        e = wf_launch_step_fast(mode, h->fast_baked, h->fast_uses_vtab && !h->vtab_stale, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
+                                env_count, slot, st);
+        if (e == cudaSuccess && h->model.amb_eps > 0.f) {  // strict FP32: FP64 re-solve of whatever the launch flagged
+            e = wf_launch_fixup64(mode, !h->vtab_stale, h->model, h->fast64, h->st, out, env_begin, env_count, slot, st);
+            h->launches += 1;
+        }
+    }
     else
         e = wf_launch_step_basic(h->cfg.precision, mode, h->model, h->st, d_mask, d_action, d_yaw, out, env_begin,
                                  env_count, st);
@@ -289,7 +327,7 @@ int wf_reset_masked(WfHandle h, const uint8_t* d_mask, const double* d_ws, const
     CUDA_TRY(launch_geometry(h, d_mask, nullptr, st));
     h->launches += 1;
     for (int k = 0; k < warmup; ++k) TRY(launch_step(h, WF_MODE_WARMUP, d_mask, nullptr, nullptr, to_ptrs(out), st));
-    return WF_OK;
+    return mark_async(h, st);
 }
 
 int wf_reset_sampled(WfHandle h, const uint8_t* d_mask, uint64_t seed, int64_t env_id_offset, double ti_lo, double ti_hi,
@@ -338,13 +376,15 @@ int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const 
 int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream) {
     if (!h || !d_action) return set_err(WF_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    return launch_step(h, WF_MODE_ENV, nullptr, d_action, nullptr, to_ptrs(out), (cudaStream_t)stream);
+    TRY(launch_step(h, WF_MODE_ENV, nullptr, d_action, nullptr, to_ptrs(out), (cudaStream_t)stream));
+    return mark_async(h, (cudaStream_t)stream);
 }
 
 int wf_update_command(WfHandle h, const double* d_yaw, const WfStepOut* out, void* stream) {
     if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    return launch_step(h, WF_MODE_INTERFACE, nullptr, nullptr, d_yaw, to_ptrs(out), (cudaStream_t)stream);
+    TRY(launch_step(h, WF_MODE_INTERFACE, nullptr, nullptr, d_yaw, to_ptrs(out), (cudaStream_t)stream));
+    return mark_async(h, (cudaStream_t)stream);
 }
 
 // Device alias of a host pointer when it is page-locked memory the GPU can address (cudaHostAlloc / cudaHostRegister
@@ -371,6 +411,9 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
                            (ho->freewind ? 2 * B : 0)) * es + (ho->truncated ? B : 0);
     if (h2d) *h2d = up;
     if (d2h) *d2h = down;
+    // run after whatever the caller queued asynchronously on its own stream (resets, wind updates, device-side steps)
+    const bool wait_async = h->ev_pending;
+    h->ev_pending = false;
 
     // ---- zero-copy path: every buffer is mapped pinned memory -> ONE launch, no copy engine.  The kernel reads the
     // commands and writes the results over PCIe itself (coalesced 128-bit / 32-bit stores from the env epilogue), so
@@ -396,6 +439,7 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
         ALIAS(z.reward, ho->reward) ALIAS(z.freewind, ho->freewind) ALIAS(z.truncated, ho->truncated)
 #undef ALIAS
         if (all) {
+            if (wait_async) CUDA_TRY(cudaStreamWaitEvent(h->host_streams[0], h->ev_async, 0));
             TRY(launch_step(h, mode, nullptr, za, zy, z, h->host_streams[0]));
             CUDA_TRY(cudaStreamSynchronize(h->host_streams[0]));
             return WF_OK;
@@ -430,12 +474,13 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
     for (int c = 0; c < nchunk; ++c) {
         const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
         cudaStream_t st = h->host_streams[c];
+        if (wait_async) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_async, 0));
         if (h_action)
             CUDA_TRY(cudaMemcpyAsync(h->d_action + b0 * T, h_action + b0 * T, sizeof(float) * nb * T, cudaMemcpyHostToDevice, st));
         if (h_yaw)
             CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd + b0 * T, h_yaw + b0 * T, sizeof(double) * nb * T, cudaMemcpyHostToDevice, st));
         TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st,
-                        (int)b0, (int)nb));
+                        (int)b0, (int)nb, c));
 #define D2H(field, per_env)                                                                                       \
     if (ho->field) {                                                                                              \
         const size_t off = b0 * (per_env), bytes = nb * (per_env);                                                \
@@ -456,8 +501,6 @@ int wf_step_host(WfHandle h, const float* h_action, const WfHostOut* ho, uint64_
 
 int wf_update_command_host(WfHandle h, const double* h_yaw, const WfHostOut* ho) {
     if (!h || !ho) return set_err(WF_ERR_INVALID, "NULL argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaDeviceSynchronize());  // order after resets / wind updates issued on other streams
     return step_host_impl(h, WF_MODE_INTERFACE, nullptr, h_yaw, ho, nullptr, nullptr);
 }
 
@@ -473,7 +516,7 @@ int wf_update_wind(WfHandle h, const uint8_t* d_mask, const double* d_ws, const 
     CUDA_TRY(launch_geometry(h, d_mask, d_cs, st, h->steps_since_wind_update >= 8));
     h->launches += 1;
     h->steps_since_wind_update = 0;
-    return WF_OK;
+    return mark_async(h, st);
 }
 
 int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream) {
@@ -481,7 +524,7 @@ int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->st.ti_amb, d_ti, sizeof(double) * h->model.B, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
-    return WF_OK;
+    return mark_async(h, (cudaStream_t)stream);
 }
 
 static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
@@ -529,7 +572,7 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64) {
         CUDA_TRY(wf_step_fast64_attributes(h->model, &attr, &ctas, &thr, &sm));
     } else if (h->cfg.kernel == WF_KERNEL_FAST) {
-        CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->st.vtab && !h->vtab_stale, h->model, &attr, &ctas, &thr, &sm));
+        CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->fast_uses_vtab && h->st.vtab && !h->vtab_stale, h->model, &attr, &ctas, &thr, &sm));
     } else {
         CUDA_TRY(wf_step_basic_attributes(h->cfg.precision, &attr, &ctas, thr));
         sm = (int)attr.sharedSizeBytes;

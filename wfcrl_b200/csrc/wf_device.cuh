@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define WF_MAX_TURBINES_K 128  // == WF_MAX_TURBINES of the public header
+#define WF_FIX_SLOTS 8  // concurrent FP32 launches of one handle (wf_step_host chunks) each own a slot of the fix-up counters
 #define WF_NP 9  // 3x3 rotor grid (case.yaml:16), p = 3*j + k with j lateral, k vertical
 
 // Model constants, passed to kernels by value (kernel parameter space = constant bank, broadcast reads).
@@ -37,6 +38,8 @@ struct WfState {
     int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
     uint8_t* amb;       // [B] FP32 kernel: 1 = a discrete decision of this solve was within the guard band of its threshold
                         //     AND could change the result (the env is re-solved by the FP64 kernel), 0 = decisions are safe
+    int* fix_list;      // [B] ids of the envs flagged by the current FP32 launch, written from index env_begin of that launch
+    int* fix_count;     // [2 * WF_FIX_SLOTS] per launch slot: number of flagged envs, number of fix-up CTAs that have left
     double* ws;         // [B] free-stream wind speed
     double* wd;         // [B] free-stream wind direction (already % 360)
     double* ws_norm;    // [B] free-stream speed of the PREVIOUS state (reward normalisation, simple_env.py:79)
@@ -61,7 +64,10 @@ struct WfState {
     // wf_vortex_table_kernel in SORTED order, so that the step kernel streams it front to back:
     //   row(i, t) for sorted source i < target t at index i*T - i*(i+1)/2 + (t - i - 1); a row is [3 columns j][3 heights k]
     //   [cVt, cVw, cWt, cWw]:  V += Gt*cVt + Gwr*cVw ;  W += max(Gt*cWt + Gwr*cWw, 0)            
-    void* vtab;         // [B][T(T-1)/2][36] float (FP32 handle) or double (FP64 handle); NULL = table disabled
+    void* vtab;         // [B][T(T-1)/2][36] rows read by the handle's own step kernel: double (FP64 handle) or float (FP32
+                        //     handle, only with WFCRL_B200_VTAB=1); NULL = that kernel evaluates every pair directly
+    double* vtab64;     // the same rows in double for the FP64 kernels: == vtab on an FP64 handle; on a strict FP32 handle a
+                        //     table of its own, read by the re-solve of the few flagged envs; NULL = disabled
     uint8_t* vtab_ok;   // [B] 1 = the env's rows match its current geometry (cleared by the geometry kernel)
     uint8_t* tab_lo;    // [B][T] per sorted source i: first t with xs[t] - xs[i] > 1e-6 m; closer targets (x-ties) are
                         //         evaluated directly from the positions, never through the table
@@ -78,6 +84,7 @@ template <typename R> struct WfFastConstT {
     R ez[6][3];        // exp(-zz^2 / eps^2)
     R cblk[48];        // the same constants packed for the kernel's shared-memory block (see build_fast_const)
     R a_top, a_bot, a_core;   // secondary steering: mean over the own grid of z/(2 pi r) * core per unit circulation
+    R inv_ss_den;             // 1 / (c_top a_top - c_bot a_bot): the steering denominator is (that) * ws * ct
     R cv[3][9], cw[3][9];     // self-induced V / W per unit (Gt, Gb, Gwr) on the own grid
     R sv[3];                  // sum over the 9 points of cv
     R D, inv_D, eps2, inv_eps2, inv_2pi;
@@ -116,8 +123,8 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
                                  int env_begin, int env_count, cudaStream_t stream);
-cudaError_t wf_launch_vortex_table(int precision, const WfModel& m, const WfFastConst64& fc, const WfState& s,
-                                   const uint8_t* d_mask, cudaStream_t stream);
+cudaError_t wf_launch_vortex_table(const WfModel& m, const WfFastConst64& fc, const WfState& s, const uint8_t* d_mask,
+                                   cudaStream_t stream);
 cudaError_t wf_launch_set_wind(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_ws,
                                const double* d_wd, cudaStream_t stream);
 cudaError_t wf_launch_sample_reset(const WfModel& m, const WfState& s, const uint8_t* d_mask, unsigned long long seed,
@@ -128,7 +135,9 @@ cudaError_t wf_launch_reset_state(const WfModel& m, const WfState& s, const uint
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads);
 cudaError_t wf_launch_step_fast(int mode, bool baked, bool use_vtab, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
+                                const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream);
+cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                              const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream);
 cudaError_t wf_step_fast_attributes(bool baked, bool use_vtab, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,

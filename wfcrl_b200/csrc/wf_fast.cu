@@ -56,7 +56,7 @@ constexpr int kMaxEvt = 8;  // ambiguous-decision records kept per env; more tha
 #endif
 #define WF_UNROLL_D WF_PRAGMA_UNROLL_(WF_FAST_UNROLL_D)
 #ifndef WF_VTAB_PF_DIST
-#define WF_VTAB_PF_DIST 2  // the table rows of source i + WF_VTAB_PF_DIST are prefetched to L2 while source i is processed
+#define WF_VTAB_PF_DIST 1  // (1 measured best: 2 -> +7 %, 4 -> +20 % step time, L2 capacity) the table rows of source i + WF_VTAB_PF_DIST are prefetched to L2 while source i is processed
 #endif
 #ifndef WF_FAST_UNROLL_T
 #define WF_FAST_UNROLL_T 2  // table passes in flight
@@ -86,7 +86,7 @@ __device__ __forceinline__ void prefetch_rows(const void* env_rows, int i, int T
 // the rows being prefetched instead of ageing through the LRU.
 __device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long pol) {
     float4 v;
-#ifdef WF_VTAB_NO_EVICT_HINT
+#ifndef WF_VTAB_EVICT_HINT  // the hint measured 3-9 % slower on B200 (profiles/r2_vortex_table.md)
     v = __ldg(p);
 #else
     asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -168,7 +168,7 @@ struct wf_false_tag { static constexpr bool value = false; };
 
 template <bool BAKED, bool VTAB>
 __global__ void __launch_bounds__(32, VTAB ? 16 : WF_FAST_MINB)
-wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const __grid_constant__ WfFastConst fc,
+wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const WfModel m, const __grid_constant__ WfFastConst fc,
                     const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
     const int b = blockIdx.x + env_begin;
@@ -250,13 +250,14 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
     // Guard band of the ONE floating-point decision that makes the solve discontinuous: a rotor point counts towards the
     // wake overlap when deficit * U0 > 0.05 m/s.  Counts are kept for both ends of the band; where they differ the event
     // is recorded and judged when the target's turbulence intensity is final (see the source prologue).
+    const bool strict = m.amb_eps > 0.f;  // flag ill-conditioned solves for the FP64 re-solve (amb_eps = 0: relaxed handle)
     const float thr_lo = 0.05f * (1.f - m.amb_eps), thr_hi = 0.05f * (1.f + m.amb_eps);
     const double two_D_d = 2.0 * m.D;
     int nevt = 0;
     bool flagged = false;
     // vortex table of this env (streamed front to back, one row per sorted pair i < t), or NULL: evaluate every pair directly
     const float4* __restrict__ vrow = nullptr;
-    if (VTAB && s.vtab_ok[b]) vrow = (const float4*)s.vtab + (size_t)b * ((size_t)T * (T - 1) / 2) * 9;
+    if (VTAB && s.vtab && s.vtab_ok[b]) vrow = (const float4*)s.vtab + (size_t)b * ((size_t)T * (T - 1) / 2) * 9;
     unsigned long long pol_stream = 0;
     if (VTAB) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     if (VTAB && vrow) {
@@ -554,7 +555,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
                 if (fabsf(ady - KC(two_D)) < 2e-3f) {  // lateral window |Y - y_i| < 2 D decided on the float-float positions
                     const double d = (((double)yt.x - (double)yi.x) + ((double)yt.y - (double)yi.y)) + (double)offj;
                     in_win = fabs(d) < two_D_d;
-                    if (fabs(fabs(d) - two_D_d) < 1e-7) flagged = true;
+                    if (strict && fabs(fabs(d) - two_D_d) < 1e-7) flagged = true;
                 }
                 if (in_win) {
                     const float wat = watK * __powf(dx * KC(inv_D), KC(ch_down));
@@ -607,6 +608,14 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         }
         const float veff = fc.rho_fac * avg * __powf(sm.cyaw[tt], fc.pP3);
         const float pw = interp_f(fc, fc.tab_pw, veff, 0.f, 0.f) * fc.ref_rho;  // [W]
+        if (strict) {
+            // Where the power curve is steep relative to the power itself (the foot of the table above cut-in, the cliff
+            // at cut-out), a rotor speed good to ~1e-5 cannot give the power to 1e-4: hand the env to the FP64 re-solve.
+            constexpr float kVelEps = 1.2e-5f;
+            const float pm = interp_f(fc, fc.tab_pw, veff * (1.f - kVelEps), 0.f, 0.f) * fc.ref_rho;
+            const float pp = interp_f(fc, fc.tab_pw, veff * (1.f + kVelEps), 0.f, 0.f) * fc.ref_rho;
+            if (fmaxf(fabsf(pp - pw), fabsf(pw - pm)) > 1e-4f * fmaxf(pw, 1.f)) flagged = true;
+        }
         float wsl = avg;
         float wdl = wd - kDeg * sdd * (1.f / 9.f);
         float loads[4] = {sm.tifin[tt], fsqrt(qu * (1.f / 9.f)), fsqrt(qv * (1.f / 9.f)), fsqrt(qw * (1.f / 9.f))};
@@ -640,8 +649,14 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
         rsum_l += __shfl_xor_sync(0xffffffffu, rsum_l, sft);
     }
     const bool any_flag = __any_sync(0xffffffffu, flagged);
+    if (lane == 0 && s.amb) s.amb[b] = (uint8_t)any_flag;
+    if (any_flag && strict) {
+        // the FP64 re-solve (wf_fixup64_kernel, next launch on this stream) redoes this env from the committed yaw state and
+        // commits the per-env epilogue state itself
+        if (lane == 0) s.fix_list[env_begin + atomicAdd(&s.fix_count[2 * slot], 1)] = b;
+        return;
+    }
     if (lane == 0) {
-        if (s.amb) s.amb[b] = (uint8_t)any_flag;
         const int it = s.num_iter[b] + 1;
         s.num_iter[b] = it;
         if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
@@ -673,7 +688,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const WfModel m, const 
 template <bool BAKED, bool VTAB>
 static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                  const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                 const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
+                                 const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream) {
     const size_t smem = fast_smem_bytes(m.T);
     static bool configured[64] = {};
     int dev = 0;
@@ -687,14 +702,14 @@ static cudaError_t launch_fast_t(int mode, const WfModel& m, const WfFastConst& 
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     static const size_t pad = getenv("WFCRL_SMEM_PAD") ? (size_t)atoi(getenv("WFCRL_SMEM_PAD")) : 0;  // tuning experiments
-    wf_step_fast_kernel<BAKED, VTAB><<<env_count, 32, smem + pad, stream>>>(mode, env_begin, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    wf_step_fast_kernel<BAKED, VTAB><<<env_count, 32, smem + pad, stream>>>(mode, env_begin, slot, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
 cudaError_t wf_launch_step_fast(int mode, bool baked, bool use_vtab, const WfModel& m, const WfFastConst& fc, const WfState& s,
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
-                                const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
-#define WF_GO(B_, V_) launch_fast_t<B_, V_>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, stream)
+                                const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream) {
+#define WF_GO(B_, V_) launch_fast_t<B_, V_>(mode, m, fc, s, d_mask, d_action, d_yaw_cmd, out, env_begin, env_count, slot, stream)
     const bool vtab = use_vtab && s.vtab != nullptr;
     return baked ? (vtab ? WF_GO(true, true) : WF_GO(true, false)) : (vtab ? WF_GO(false, true) : WF_GO(false, false));
 #undef WF_GO

@@ -27,10 +27,10 @@ constexpr double kNumEps = 0.001;
 constexpr int kTurbPerPass = 10;
 
 // see wf_fast.cu: pull the vortex-table rows of sorted source `i` into L2 ahead of their use (one bulk prefetch)
-__device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int T, int lane) {
+__device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int T, int lane, unsigned row_bytes) {
     if (i >= T - 1 || lane != 0) return;
-    const char* p = (const char*)env_rows + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 288;
-    const unsigned bytes = (unsigned)(T - 1 - i) * 288;
+    const char* p = (const char*)env_rows + ((size_t)i * T - (size_t)i * (i + 1) / 2) * row_bytes;
+    const unsigned bytes = (unsigned)(T - 1 - i) * row_bytes;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
@@ -98,14 +98,26 @@ __device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T) {
     return s;
 }
 
-__global__ void __launch_bounds__(32, 4)
-wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
-                      const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
-                      const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
-    const int b = blockIdx.x + env_begin;
-    if (mask && !mask[b]) return;
+// Load the 12 vortex-table coefficients of one (pair, lateral column) as doubles: [k][cVt, cVw, cWt, cWw].
+__device__ __forceinline__ void load_row12(const double* __restrict__ p, double* c) {
+    const double2* q = (const double2*)p;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { const double2 v = __ldg(q + e); c[2 * e] = v.x; c[2 * e + 1] = v.y; }
+}
+// One env solved in FP64 by W warps (a CTA of 32 W threads).
+//   W = 1: the throughput configuration of the bit-check mode (one warp = one CTA = one env, compacted deficit queue).
+//   W > 1: the low-latency configuration used to re-solve the envs an FP32 launch flagged: every warp evaluates the source's
+//          scalar chain itself (no broadcast), then the W warps share the targets of ONE fused vortex + deficit pass.
+// OutT = type of the caller's output buffers (double for an FP64 handle, float for the re-solve on an FP32 handle).  FIX = re-solve: the FP32 kernel has already applied the action (yaw and
+// accumulators are committed) but none of the per-env epilogue state, which is committed here.
+template <int W, typename OutT, bool FIX>
+__device__ __forceinline__ void solve_env64(const int b, const int mode, const bool use_vtab, const WfModel& m,
+                                            const WfFastConst64& fc, const WfState& s, const float* __restrict__ action,
+                                            const double* __restrict__ yaw_cmd, const WfOutPtrs& out) {
     const int T = m.T;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = 32 * W;
+    auto csync = [] { if (W == 1) __syncwarp(); else __syncthreads(); };
     const size_t row = (size_t)b * T;
     extern __shared__ __align__(16) unsigned char smem_raw64[];
     const SmemView64 sm = carve64(smem_raw64, T);
@@ -113,9 +125,9 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
     // ---- env prologue on the ORIGINAL turbine order (mdp.py:291-319, simple_env.py:64-72) -------------------------
     int nm = 0;
     if (mode == WF_MODE_ENV) nm = s.num_moves[b] + 1;
-    for (int tt = lane; tt < T; tt += 32) {
+    for (int tt = tid; tt < T; tt += NT) {
         double ynew;
-        if (mode == WF_MODE_ENV) {
+        if (!FIX && mode == WF_MODE_ENV) {
             float a = action[row + tt];
             const float acc = s.acc[row + tt];
             const float acc_c = (m.multi_agent && tt != T - 1) ? s.acc_prev[row + tt] : acc;
@@ -129,7 +141,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
             s.acc[row + tt] = __fadd_rn(acc, fabsf(a));
             ynew = (double)y1;
             s.yaw[row + tt] = ynew;
-        } else if (mode == WF_MODE_INTERFACE && yaw_cmd) {
+        } else if (!FIX && mode == WF_MODE_INTERFACE && yaw_cmd) {
             ynew = yaw_cmd[row + tt];
             s.yaw[row + tt] = ynew;
         } else {
@@ -143,10 +155,10 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
         sm.idx[tt] = s.idx[row + tt];
         sm.ordr[tt] = (unsigned char)s.order[row + tt];
     }
-    for (int q = lane; q < 9 * T; q += 32) { sm.wsq[q] = 0.0; sm.vw[q] = make_double2(0.0, 0.0); }
-    for (int q = lane; q < 3 * T; q += 32) sm.tia[q] = 0.0;
-    __syncwarp();
-    for (int tt = lane; tt < T; tt += 32) {
+    for (int q = tid; q < 9 * T; q += NT) { sm.wsq[q] = 0.0; sm.vw[q] = make_double2(0.0, 0.0); }
+    for (int q = tid; q < 3 * T; q += NT) sm.tia[q] = 0.0;
+    csync();
+    for (int tt = tid; tt < T; tt += NT) {
         const double yd = sm.ynew[sm.ordr[tt]];
         double sy, cy;
         sincos(yd * kRad, &sy, &cy);
@@ -157,10 +169,11 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
     const double ws = s.ws[b], wd = s.wd[b];
     const double I0 = s.ti_amb[b];
     const double I02 = I0 * I0;
-    const double I0p = pow(I0, fc.ch_init);
+    const double I0p = exp(fc.ch_init * log(I0));
+    const double rws = 1.0 / ws;
     const double U0a = ws * fc.ratio[0], U0b = ws * fc.ratio[1], U0c = ws * fc.ratio[2];
     const double D = fc.D;
-    __syncwarp();
+    csync();
 
     const int g = lane / 3, j = lane - 3 * g;
     const bool lane_ok = lane < 3 * kTurbPerPass;
@@ -174,13 +187,13 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
     const double c_dec = fc.eps2 * fc.inv_2pi;
     const double eps2 = fc.eps2;
     // vortex table of this env (wf_device.cuh), or NULL: evaluate every pair directly
-    const double2* __restrict__ vrow = nullptr;
-    if (use_vtab && s.vtab && s.vtab_ok[b]) vrow = (const double2*)s.vtab + (size_t)b * ((size_t)T * (T - 1) / 2) * 18;
-    if (vrow) { prefetch_rows64(vrow, 0, T, lane); prefetch_rows64(vrow, 1, T, lane); }
+    const double* __restrict__ vrow = nullptr;
+    if (use_vtab && s.vtab64 && s.vtab_ok[b]) vrow = s.vtab64 + (size_t)b * ((size_t)T * (T - 1) / 2) * 36;
+    if (vrow && warp == 0) { prefetch_rows64(vrow, 0, T, lane, 288); prefetch_rows64(vrow, 1, T, lane, 288); }
 
     for (int i = 0; i < T; ++i) {
-        if (vrow) prefetch_rows64(vrow, i + 2, T, lane);
-        // ===== source prologue =====
+        if (vrow && warp == 0) prefetch_rows64(vrow, i + 2, T, lane, 288);
+        // ===== source prologue (every warp on its own: all values below are block-uniform) =====
         double su3, sv, sw, vq, wwq;
         {
             const double wq = sm.wsq[9 * i + plc];
@@ -202,42 +215,71 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
         const double ct_raw = dclamp(interp_d(fc, fc.tab_ct, avg, 0.0001, 0.9999), 0.0001, 0.9999);
         const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.yawd[i];
         const double ct = ct_raw * cy;
-        const double a = 0.5 / cy * (1.0 - sqrt(1.0 - ct * cy));
+        // The chain below is the critical path of the FP64 kernels (one warp, dependent double-precision operations): divisions
+        // are shared through reciprocals and identities that hold to rounding (1e-16, the tolerance is 1e-9) are used freely.
+        const double rcy = 1.0 / cy, rct = 1.0 / ct;
+        const double a = 0.5 * rcy * (1.0 - sqrt(1.0 - ct * cy));
         const double Gtop0 = fc.c_top * ws * ct, Gbot0 = fc.c_bot * ws * ct;
         const double Gwr = fc.c_wr * (a - a * a) * avg;
         const double Gt = sy * cy * Gtop0, Gb = -(sy * cy * Gbot0);
 
-        // A.5 secondary steering through the per-model grid integrals
-        double val = 2.0 * (sv / 9.0 - Gwr * fc.a_core) / (Gtop0 * fc.a_top - Gbot0 * fc.a_bot);
+        // A.5 secondary steering through the per-model grid integrals (the denominator is (c_top a_top - c_bot a_bot) ws ct)
+        double val = 2.0 * (sv * (1.0 / 9.0) - Gwr * fc.a_core) * (rct * fc.inv_ss_den) * rws;
         val = dclamp(val, -1.0, 1.0);
         const double g_deg = -(yd + kDeg * (0.5 * asin(val)));  // minus the effective yaw, degrees
         const double g_rad = g_deg * kRad;
         const double cg = cos(g_rad);
+        const double rcg = 1.0 / cg;
 
-        // A.6 deflection scalars
+        // A.6 deflection scalars.  M0 = C0 (2 - C0) = 1 - (1 - C0)^2 = ct.
         const double sq1ct = sqrt(1.0 - ct);
         const double sqcg = sqrt(1.0 - ct * cg);
         const double sz0d = 0.5 * D * sqrt((1.0 + sqcg) / (2.0 * (1.0 + sq1ct)));
         const double sy0d = sz0d * cg;
         const double C0 = 1.0 - sq1ct;
-        const double M0 = C0 * (2.0 - C0);
         const double E0 = C0 * C0 - fc.e3_112 * C0 + fc.e3_13;
-        const double th = fc.dm03 * g_rad / cg * (1.0 - sqcg);
-        const double sM0 = sqrt(M0);
-        const double tan_th = tan(th);
-        const double Kc = th * E0 / 5.2 * sqrt(sy0d * sz0d / M0);
+        const double th = fc.dm03 * g_rad * rcg * (1.0 - sqcg);
+        const double sM0 = sqrt(ct);
+        double tan_th;
+        if (fabs(th) < 0.35) {
+            // always taken for yaw within +-40 deg (|th| <= 0.31).  Maclaurin series of tan up to th^25 -- coefficients
+            // 2^2n (2^2n - 1) |B_2n| / (2n)! -- good to 2.3e-16 relative on the interval (checked against libm); an eighth of
+            // the instructions of tan() on the critical path
+            const double t2 = th * th;
+            double p = 0x1.0b132d39a6050p-16;
+            p = p * t2 + 0x1.497d8eea25259p-15;
+            p = p * t2 + 0x1.967e18afcafadp-14;
+            p = p * t2 + 0x1.f57d7734d1664p-13;
+            p = p * t2 + 0x1.3558248036744p-11;
+            p = p * t2 + 0x1.7da36452b75e3p-10;
+            p = p * t2 + 0x1.d6d3d0e157de0p-9;
+            p = p * t2 + 0x1.226e355e6c23dp-7;
+            p = p * t2 + 0x1.664f4882c10fap-6;
+            p = p * t2 + 0x1.ba1ba1ba1ba1cp-5;
+            p = p * t2 + 0x1.1111111111111p-3;
+            p = p * t2 + 0x1.5555555555555p-2;
+            tan_th = th + th * (t2 * p);
+        } else {
+            tan_th = tan(th);
+        }
+        const double Kc = th * E0 * (1.0 / 5.2) * sqrt(sy0d * sz0d * rct);
         const double A_ln = (1.6 + sM0) / (1.6 - sM0);
         const double inv_s0d = 1.0 / (sy0d * sz0d);
 
-        const double ta0 = sm.tia[3 * i], ta1 = sm.tia[3 * i + 1], ta2 = sm.tia[3 * i + 2];
-        const double tp0 = sqrt(ta0 * ta0 + I02), tp1 = sqrt(ta1 * ta1 + I02), tp2 = sqrt(ta2 * ta2 + I02);
-        const double tpre = (j == 0) ? tp0 : ((j == 1) ? tp1 : tp2);
+        // ambient + wake-added TI per lateral column: every lane evaluates its own column, the three values travel by shuffle
+        const double ta_j = sm.tia[3 * i + j];
+        const double tp_j = sqrt(ta_j * ta_j + I02);
+        const double tp0 = __shfl_sync(0xffffffffu, tp_j, 0), tp1 = __shfl_sync(0xffffffffu, tp_j, 1),
+                     tp2 = __shfl_sync(0xffffffffu, tp_j, 2);
+        const double tpre = tp_j;
         const double beta_term = fc.beta2 * (1.0 - sq1ct);
-        const double x0d = D * cg * (1.0 + sqcg) / (1.4142135623730951 * (fc.alpha4 * tpre + beta_term));
+        // x0 = N / Dn and 1 / x0 = Dn / N from one division
+        const double x0d_n = D * cg * (1.0 + sqcg), x0d_d = 1.4142135623730951 * (fc.alpha4 * tpre + beta_term);
+        const double x0d_r = 1.0 / (x0d_n * x0d_d);
+        const double x0d = x0d_n * x0d_n * x0d_r, inv_x0d = x0d_d * x0d_d * x0d_r;
         const double kyd = fc.ka * tpre + fc.kb;
         const double delta0 = tan_th * x0d;
         const double Kck = Kc / kyd;
-        const double inv_x0d = 1.0 / x0d;
 
         // own transverse velocities + yaw-added recovery (in-place TI update)
         const uchar4 ix = sm.idx[i];
@@ -251,53 +293,39 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
 #pragma unroll
             for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
             sumW += rw;
-            __syncwarp();
-            if (lane < 9) sm.vw[9 * i + lane] = make_double2(vq + Vs, wwq + Ws);
+            csync();  // every reader of this turbine's (v, w) above is done (self_on is block-uniform)
+            if (tid < 9) sm.vw[9 * i + tid] = make_double2(vq + Vs, wwq + Ws);
         }
         const double aI = avg * tp0;
         const double kk2 = 3.0 * aI * aI;
-        const double v_term = sumV / 9.0, w_term = sumW / 9.0;
+        const double v_term = sumV * (1.0 / 9.0), w_term = sumW * (1.0 / 9.0);
         const double k_total = 0.5 * (kk2 + v_term * v_term + w_term * w_term);
         const double I_mix = sqrt((2.0 / 3.0) * k_total) / avg - tp0;
         const double tq0 = tp0 + 2.0 * I_mix, tq1 = tp1 + 2.0 * I_mix, tq2 = tp2 + 2.0 * I_mix;
-        if (lane == 0) sm.tifin[i] = ((tq0 + tq1) + tq2) / 3.0;
+        if (tid == 0) sm.tifin[i] = ((tq0 + tq1) + tq2) / 3.0;
         const double tpost = (j == 0) ? tq0 : ((j == 1) ? tq1 : tq2);
 
         // A.8 velocity-model scalars with the updated TI
-        const double x0v = D * cy * (1.0 + sq1ct) / (1.4142135623730951 * (fc.alpha4 * tpost + beta_term));
+        const double x0v_n = D * cy * (1.0 + sq1ct), x0v_d = 1.4142135623730951 * (fc.alpha4 * tpost + beta_term);
+        const double x0v_r = 1.0 / (x0v_n * x0v_d);
+        const double x0v = x0v_n * x0v_n * x0v_r, inv_x0v = x0v_d * x0v_d * x0v_r;
         const double kyv = fc.ka * tpost + fc.kb;
-        const double inv_x0v = 1.0 / x0v;
         const double sz0v = fc.near_c * (0.5 / 0.501);
         const double sy0v = sz0v * cy;
-        const double near_s = fc.near_c * sqrt(ct);
+        const double near_s = fc.near_c * sM0;
         const double ctc = ct * cy * fc.d2_8;
-        const double watK = fc.ch_const * pow(a, fc.ch_ai) * I0p;
+        const double watK = fc.ch_const * exp(fc.ch_ai * log(a)) * I0p;  // a^ai (pow(): 3x the instructions, same to 1e-15)
 
         const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
         const double x_i = sm.xi[i], y_i = sm.yi[i];
 
         constexpr double kCut = 9.5;
         const double reach1 = kCut * kyv;
-        const double reach0 = kCut * fmax(near_s, sy0v) + fabs(delta0) + fabs(Kck) * log(A_ln);
+        // (a conservative cut-off: single precision is plenty for the logarithm)
+        const double reach0 = kCut * fmax(near_s, sy0v) + fabs(delta0) + fabs(Kck) * (double)(__logf((float)A_ln) * 1.0001f);
 
-        // ===== V sweep =====
-        int qn = 0;
-        const int t_hi = vrow ? (int)s.tab_lo[row + i] : T;  // with the table only the x-ties take the direct path
-#pragma unroll 1
-        for (int t0 = lo; t0 < ((t_hi - lo > 1 || !vrow) ? t_hi : lo); t0 += kTurbPerPass) {  // without ties [lo, t_hi) = {i}
-            const int tr = t0 + g;
-            const bool active = lane_ok && tr < t_hi && tr != i;
-            const int t = min(tr, T - 1);
-            const double dx = sm.xs[t] - x_i;
-            const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
-
-            const bool need = active && (t >= near_i) && (fabs(dyc) < reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad));
-            const unsigned nb = __ballot_sync(0xffffffffu, need);
-            const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
-            const unsigned lb = __ballot_sync(0xffffffffu, leader);
-            if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
-            qn += __popc(lb);
-
+        // --- transverse velocities of source i on the 3 vertical points of (target t, column j), evaluated directly
+        auto v_direct = [&](const int t, const double dx, const double dyc, const bool active) {
             const double yL = dyc + kNumEps;
             const double q = yL * yL;
             const double E = exp(-q * fc.inv_eps2);
@@ -331,48 +359,24 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
                     sm.vw[qb + k] = make_double2(o.x + Vk[k], o.y + Wk[k]);
                 }
             }
-        }
-        if (vrow) {
-            // V sweep through the table: V += Gt*cVt + Gwr*cVw ; W += max(Gt*cWt + Gwr*cWw, 0); a lane streams the 96
-            // contiguous bytes of its (target, column)
-            const double2* __restrict__ src = vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 18 + 6 * j;
-#pragma unroll 2
-            for (int t0 = t_hi; t0 < T; t0 += kTurbPerPass) {
-                const int tr = t0 + g;
-                const bool active = lane_ok && tr < T;
-                const int t = min(tr, T - 1);
-                const double2* __restrict__ rp = src + (size_t)(t - i - 1) * 18;
-                double2 c[6];
+        };
+        // --- the same through the table row of the sorted pair (i, t): V += Gt*cVt + Gwr*cVw ; W += max(Gt*cWt + Gwr*cWw, 0)
+        auto v_table = [&](const int t, const bool active) {
+            double c[12];
+            load_row12(vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2 + (size_t)(t - i - 1)) * 36 + 12 * j, c);
+            if (active) {
+                const int qb = 9 * t + 3 * j;
 #pragma unroll
-                for (int e = 0; e < 6; ++e) c[e] = __ldg(rp + e);
-                const double dx = sm.xs[t] - x_i;
-                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
-                const bool need = active && (t >= near_i) && (fabs(dyc) < reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad));
-                const unsigned nb = __ballot_sync(0xffffffffu, need);
-                const bool leader = (j == 0) && active && (((nb >> (3 * g)) & 7u) != 0u);
-                const unsigned lb = __ballot_sync(0xffffffffu, leader);
-                if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
-                qn += __popc(lb);
-                if (active) {
-                    const int qb = 9 * t + 3 * j;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const double2 o = sm.vw[qb + k];
-                        sm.vw[qb + k] = make_double2(o.x + (Gt * c[2 * k].x + Gwr * c[2 * k].y),
-                                                     o.y + fmax(Gt * c[2 * k + 1].x + Gwr * c[2 * k + 1].y, 0.0));
-                    }
+                for (int k = 0; k < 3; ++k) {
+                    const double2 o = sm.vw[qb + k];
+                    sm.vw[qb + k] = make_double2(o.x + (Gt * c[4 * k] + Gwr * c[4 * k + 1]),
+                                                 o.y + fmax(Gt * c[4 * k + 2] + Gwr * c[4 * k + 3], 0.0));
                 }
             }
-        }
-        __syncwarp();
-
-        // ===== D sweep =====
-        for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
-            const int e = q0 + g;
-            const bool active = lane_ok && e < qn;
-            const int t = sm.queue[min(e, qn - 1)];
-            const double dx = sm.xs[t] - x_i;
-            const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+        };
+        // --- deflection, Gaussian deficit, sum of squares, overlap count and wake-added TI of source i on (target t, column j);
+        //     the 3 lanes of a target must call it together (the overlap count is summed over the columns)
+        auto d_apply = [&](const int t, const double dx, const double dyc, const bool active) {
             const double lin = fc.bd * dx + fc.ad;
             double defl;
             if (dx <= x0d) {
@@ -413,15 +417,79 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
                               __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
             if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabs(dyc) < fc.two_D) {
                 const double dxp = dx + ((dx <= 0.1) ? 1.0 : 0.0);
-                const double wat = watK * pow(dxp / D, fc.ch_down);
+                const double wat = watK * exp(fc.ch_down * log(dxp / D));
                 const double ta = ((double)c_tot / 9.0) * wat;
                 sm.tia[3 * t + j] = fmax(sm.tia[3 * t + j], ta);
             }
+        };
+        auto reach = [&](const double dx) { return reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad); };
+        const int t_hi = vrow ? (int)s.tab_lo[row + i] : T;  // with the table only the x-ties take the direct path
+
+        if (W == 1) {
+            // ===== V sweep over all downstream targets (builds the compacted queue), then D sweep over the queue =====
+            int qn = 0;
+            auto enqueue = [&](const int t, const bool need) {
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                const bool leader = (j == 0) && (((nb >> (3 * g)) & 7u) != 0u) && lane_ok;
+                const unsigned lb = __ballot_sync(0xffffffffu, leader);
+                if (leader) sm.queue[qn + __popc(lb & ((1u << lane) - 1u))] = (unsigned char)t;
+                qn += __popc(lb);
+            };
+#pragma unroll 1
+            for (int t0 = lo; t0 < ((t_hi - lo > 1 || !vrow) ? t_hi : lo); t0 += kTurbPerPass) {  // without ties [lo, t_hi) = {i}
+                const int tr = t0 + g;
+                const bool active = lane_ok && tr < t_hi && tr != i;
+                const int t = min(tr, T - 1);
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                enqueue(t, active && (t >= near_i) && (fabs(dyc) < reach(dx)));
+                v_direct(t, dx, dyc, active);
+            }
+            if (vrow) {
+#pragma unroll 2
+                for (int t0 = t_hi; t0 < T; t0 += kTurbPerPass) {
+                    const int tr = t0 + g;
+                    const bool active = lane_ok && tr < T;
+                    const int t = min(tr, T - 1);
+                    const double dx = sm.xs[t] - x_i;
+                    const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                    enqueue(t, active && (t >= near_i) && (fabs(dyc) < reach(dx)));
+                    v_table(t, active);
+                }
+            }
+            __syncwarp();
+            for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
+                const int e = q0 + g;
+                const bool active = lane_ok && e < qn;
+                const int t = sm.queue[min(e, qn - 1)];
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                d_apply(t, dx, dyc, active);
+            }
+            __syncwarp();
+        } else {
+            // ===== one fused pass: warp w takes targets t0 + 10 w .. t0 + 10 w + 9; the deficit part runs where some column
+            //       of the target is within reach of the wake =====
+#pragma unroll 1
+            for (int t0 = lo; t0 < T; t0 += kTurbPerPass * W) {
+                const int tr = t0 + kTurbPerPass * warp + g;
+                const bool active = lane_ok && tr < T && tr != i;
+                const int t = min(tr, T - 1);
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                const bool tab = vrow && t >= t_hi;
+                if (__any_sync(0xffffffffu, active && !tab)) v_direct(t, dx, dyc, active && !tab);
+                if (tab) v_table(t, active);
+                const bool need = active && (t >= near_i) && (fabs(dyc) < reach(dx));
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                if (nb) d_apply(t, dx, dyc, active && (((nb >> (3 * g)) & 7u) != 0u));
+            }
+            __syncthreads();
         }
-        __syncwarp();
     }
 
-    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    // ---- epilogue (first warp) ------------------------------------------------------------------------------------------
+    if (warp != 0) return;
     const bool env = (mode != WF_MODE_INTERFACE);
     double rsum_p = 0.0, rsum_l = 0.0;
     for (int tt = lane; tt < T; tt += 32) {
@@ -479,13 +547,13 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
             yv = dclamp(yv, (double)m.yaw_lo_f, (double)m.yaw_hi_f);
         }
         const size_t o = row + orig;
-        if (out.yaw) ((double*)out.yaw)[o] = yv;
-        if (out.wind_speed) ((double*)out.wind_speed)[o] = wsl;
-        if (out.wind_direction) ((double*)out.wind_direction)[o] = wdl;
-        if (out.power) ((double*)out.power)[o] = p_out;
+        if (out.yaw) ((OutT*)out.yaw)[o] = (OutT)yv;
+        if (out.wind_speed) ((OutT*)out.wind_speed)[o] = (OutT)wsl;
+        if (out.wind_direction) ((OutT*)out.wind_direction)[o] = (OutT)wdl;
+        if (out.power) ((OutT*)out.power)[o] = (OutT)p_out;
         if (out.load) {
-            double* Lp = (double*)out.load + 4 * o;
-            Lp[0] = loads[0]; Lp[1] = loads[1]; Lp[2] = loads[2]; Lp[3] = loads[3];
+            OutT* Lp = (OutT*)out.load + 4 * o;
+            Lp[0] = (OutT)loads[0]; Lp[1] = (OutT)loads[1]; Lp[2] = (OutT)loads[2]; Lp[3] = (OutT)loads[3];
         }
     }
 #pragma unroll
@@ -499,7 +567,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
         if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
         double fw0 = ws, fw1 = wd;
         if (mode == WF_MODE_WARMUP) { fw0 = dclamp(fw0, 3.0, 28.0); fw1 = dclamp(fw1, 0.0, 360.0); }
-        if (out.freewind) { ((double*)out.freewind)[2 * b] = fw0; ((double*)out.freewind)[2 * b + 1] = fw1; }
+        if (out.freewind) { ((OutT*)out.freewind)[2 * b] = (OutT)fw0; ((OutT*)out.freewind)[2 * b + 1] = (OutT)fw1; }
         if (mode == WF_MODE_ENV) {
             s.num_moves[b] = nm;
             const double wn = s.ws_norm[b];
@@ -513,13 +581,59 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
                 reward = shaped;
             }
             if (!isfinite(reward)) s.nonfinite[b] += 1;
-            if (out.reward) ((double*)out.reward)[b] = reward;
+            if (out.reward) ((OutT*)out.reward)[b] = (OutT)reward;
             s.ws_norm[b] = ws;
         }
     }
 }
 
+__global__ void __launch_bounds__(32, 4)
+wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
+                      const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
+                      const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
+    const int b = blockIdx.x + env_begin;
+    if (mask && !mask[b]) return;
+    solve_env64<1, double, false>(b, mode, use_vtab, m, fc, s, action, yaw_cmd, out);
+}
+
+// Re-solve, in FP64, of the envs an FP32 launch flagged (their ids sit in s.fix_list[env_begin ...], their number in
+// s.fix_count[2 slot]); launched right behind every FP32 step launch of a strict handle, usually with nothing or a handful of
+// envs to do, so it is built for latency: kFixWarps warps per env.  The last CTA to leave re-arms the counters.
+constexpr int kFixWarps = 4;
+__global__ void __launch_bounds__(32 * kFixWarps, 1)
+wf_fixup64_kernel(const int mode, const int env_begin, const int slot, const bool use_vtab, const WfModel m,
+                  const __grid_constant__ WfFastConst64 fc, const WfState s, const WfOutPtrs out) {
+    const int n = *(volatile int*)&s.fix_count[2 * slot];
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        solve_env64<kFixWarps, float, true>(s.fix_list[env_begin + k], mode, use_vtab, m, fc, s, nullptr, nullptr, out);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&s.fix_count[2 * slot + 1], 1) == (int)gridDim.x - 1) {
+            s.fix_count[2 * slot] = 0;
+            s.fix_count[2 * slot + 1] = 0;
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                              const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream) {
+    const size_t smem = fast64_smem_bytes(m.T);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(wf_fixup64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const int grid = env_count < 296 ? env_count : 296;  // flagged envs are rare: two CTAs per SM cover any realistic count
+    wf_fixup64_kernel<<<grid, 32 * kFixWarps, smem, stream>>>(mode, env_begin, slot, use_vtab, m, fc, s, out);
+    return cudaGetLastError();
+}
 
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,

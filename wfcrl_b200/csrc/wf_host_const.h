@@ -114,6 +114,7 @@ template <typename R> static inline void build_fast_const(const WfConfig& c, WfF
     f->c_top = (R)((PI / 8) * D * vel_top * mean_ratio);
     f->c_bot = (R)((PI / 8) * D * vel_bot * mean_ratio);
     f->c_wr = (R)(0.25 * 2 * PI * D / c.tsr);
+    f->inv_ss_den = (R)(1.0 / (((PI / 8) * D * vel_top * mean_ratio) * a_top - ((PI / 8) * D * vel_bot * mean_ratio) * a_bot));
     f->alpha4 = (R)(4 * c.alpha); f->beta2 = (R)(2 * c.beta); f->ka = (R)c.ka; f->kb = (R)c.kb;
     f->ad = (R)c.ad; f->bd = (R)c.bd; f->dm03 = (R)(0.3 * c.dm);
     f->e3_112 = (R)(3 * exp(1.0 / 12.0)); f->e3_13 = (R)(3 * exp(1.0 / 3.0));

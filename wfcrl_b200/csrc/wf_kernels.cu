@@ -238,7 +238,6 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
 // Evaluated in FP64 with the accurate math functions whatever the handle's precision; stored as R.
 // One CTA per env; a thread owns one (row, lateral column) and writes its 12 coefficients [k][cVt, cVw, cWt, cWw].
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R>
 __global__ void __launch_bounds__(256)
 wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc, const WfState s,
                        const uint8_t* __restrict__ mask) {
@@ -257,7 +256,8 @@ wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc
     }
     __syncthreads();
     const int rows = T * (T - 1) / 2;
-    R* __restrict__ tab = (R*)s.vtab + (size_t)b * rows * 36;
+    double* __restrict__ tab64 = s.vtab64 ? s.vtab64 + (size_t)b * rows * 36 : nullptr;
+    float* __restrict__ tab32 = (s.vtab && (void*)s.vtab != (void*)s.vtab64) ? (float*)s.vtab + (size_t)b * rows * 36 : nullptr;
     const double rho = fc.c_bot / fc.c_top;  // Gb = -rho * Gt
     const double c_dec = fc.eps2 * fc.inv_2pi;
     for (int task = threadIdx.x; task < rows * 3; task += blockDim.x) {
@@ -274,7 +274,7 @@ wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc
         const double yL = dyc + kNumEps;
         const double q = yL * yL;
         const double E = exp(-q * fc.inv_eps2);
-        R* dst = tab + (size_t)row * 36 + j * 12;
+        const size_t dst = (size_t)row * 36 + j * 12;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             double A[3], Bc[3];  // per unit circulation of (top pair, bottom pair, wake-rotation pair): V and W sums
@@ -287,10 +287,12 @@ wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc
                 Bc[pr] = fa - fb;
             }
             const double dec = c_dec / (fc.nu4[k] * dx + fc.eps2);
-            dst[4 * k + 0] = (R)(dec * (A[0] - rho * A[1]));
-            dst[4 * k + 1] = (R)(dec * A[2]);
-            dst[4 * k + 2] = (R)(-yL * dec * (Bc[0] - rho * Bc[1]));
-            dst[4 * k + 3] = (R)(-yL * dec * Bc[2]);
+            const double c4[4] = {dec * (A[0] - rho * A[1]), dec * A[2], -yL * dec * (Bc[0] - rho * Bc[1]), -yL * dec * Bc[2]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (tab64) tab64[dst + 4 * k + e] = c4[e];
+                if (tab32) tab32[dst + 4 * k + e] = (float)c4[e];
+            }
         }
     }
     __syncthreads();
@@ -370,7 +372,9 @@ __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const ui
         s.ws_norm[b] = fmin(fmax(w, 3.0), 28.0);  // start_state is clipped to the observation space (mdp.py:266)
         s.num_iter[b] = 0;
         s.num_moves[b] = 0;
-        s.shaper_ref[b] = m.shaper_reference;
+        // WindFarmEnv.reset calls reward_shaper.reset(), and StepPercentage.reset() puts its reference back to 0.0 whatever
+        // the constructor argument was (rewards.py:45-46): the first shaped reward of every episode is 0
+        s.shaper_ref[b] = 0.0;
     }
 }
 
@@ -803,11 +807,10 @@ cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_vortex_table(int precision, const WfModel& m, const WfFastConst64& fc, const WfState& s,
-                                   const uint8_t* d_mask, cudaStream_t stream) {
-    if (!s.vtab || m.T < 2) return cudaSuccess;
-    if (precision == 0) wf_vortex_table_kernel<double><<<m.B, 256, 0, stream>>>(m, fc, s, d_mask);
-    else wf_vortex_table_kernel<float><<<m.B, 256, 0, stream>>>(m, fc, s, d_mask);
+cudaError_t wf_launch_vortex_table(const WfModel& m, const WfFastConst64& fc, const WfState& s, const uint8_t* d_mask,
+                                   cudaStream_t stream) {
+    if ((!s.vtab && !s.vtab64) || m.T < 2) return cudaSuccess;
+    wf_vortex_table_kernel<<<m.B, 256, 0, stream>>>(m, fc, s, d_mask);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,13 @@ _OBS_BOUNDS = {"wind_speed": (3.0, 28.0), "wind_direction": (0.0, 360.0)}
 
 
 class VecWindFarmEnv:
+    """``num_envs`` copies of one ``*_Floris`` env on one GPU (see the module docstring).
+
+    ALIASING: ``reset`` / ``step`` return observation, reward, ``info["power"]`` and ``info["load"]`` as VIEWS of the
+    backend's output buffers, which the next ``step`` overwrites in place (and, on auto-reset steps, the warm-up solve of
+    the restarted envs already has).  A rollout buffer must ``.clone()`` what it keeps, or construct the env with
+    ``copy_outputs=True`` to get fresh tensors from every call (one extra device copy of ~10 floats per turbine)."""
+
     metadata = {"name": "vectorized-windfarm"}
 
     def __init__(self, layout: Union[str, Dict], num_envs: int, *, device: int = 0, precision: str = "f32",
@@ -35,8 +42,9 @@ class VecWindFarmEnv:
                  reward_shaper: Optional[RewardShaper] = None, max_num_steps: int = 500, load_coef: float = 0.1,
                  start_iter: int = 0, auto_reset: bool = True, multi_agent: bool = False, env_id_offset: int = 0,
                  wind_time_series: Optional[Union[str, np.ndarray]] = None, exact_host_trig: Optional[bool] = None,
-                 turbulence_intensity_range: Optional[tuple] = None):
+                 turbulence_intensity_range: Optional[tuple] = None, copy_outputs: bool = False):
         case = get_layout(layout) if isinstance(layout, str) else layout
+        self.copy_outputs = bool(copy_outputs)
         self.farm_case = case
         self.num_envs = int(num_envs)
         self.num_turbines = case["num_turbines"]
@@ -105,21 +113,26 @@ class VecWindFarmEnv:
         self._needs_reset = True
 
     # -- wind sampling ------------------------------------------------------------------------------------------
-    def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray):
+    def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray, need_speed: bool = True,
+                         need_direction: bool = True):
         """The reference's reset distribution with numpy's Generator, one stream per GLOBAL env id
-        (wfcrl/mdp.py:235-258): bit-identical to what ``WindFarmMDP.reset(seed + env_id)`` would draw."""
+        (wfcrl/mdp.py:235-258): bit-identical to what ``WindFarmMDP.reset(seed + env_id)`` would draw.  A component the
+        caller supplies through ``options`` is not drawn at all, so the other one keeps its place in the stream."""
         ws = np.empty(len(env_ids))
         wd = np.empty(len(env_ids))
         for k, b in enumerate(env_ids):
             rng = np.random.default_rng(None if seed is None else seed + self.env_id_offset + int(b))
-            ws[k] = np.clip(8 * rng.weibull(8), 3, 28)
-            wd[k] = np.clip(rng.normal(270, 20) % 360, 0, 360)
+            if need_speed:
+                ws[k] = np.clip(8 * rng.weibull(8), 3, 28)
+            if need_direction:
+                wd[k] = np.clip(rng.normal(270, 20) % 360, 0, 360)
         return ws, wd
 
     # -- API ------------------------------------------------------------------------------------------------------
     def _obs(self, out):
-        return OrderedDict([("yaw", out["yaw"]), ("freewind_measurements", out["freewind"]),
-                            ("wind_speed", out["wind_speed"]), ("wind_direction", out["wind_direction"])])
+        c = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
+        return OrderedDict([("yaw", c(out["yaw"])), ("freewind_measurements", c(out["freewind"])),
+                            ("wind_speed", c(out["wind_speed"])), ("wind_direction", c(out["wind_direction"]))])
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None, env_ids=None):
         """Reset all (or ``env_ids``) envs.  ``options`` may carry ``wind_speed`` / ``wind_direction`` (scalars or
@@ -138,10 +151,11 @@ class VecWindFarmEnv:
             episode[ids] = 0
             self.backend.set_state("episode", episode)
         given = "wind_speed" in options and "wind_direction" in options
+        any_given = "wind_speed" in options or "wind_direction" in options
         if self._series is not None:
             start = np.random.randint(0, self._series.shape[0], size=len(ids))  # interface.py:517
             self._series_pos[idt] = torch.as_tensor(start, device=self.device)
-        if seed is None and not given and self._series is None:
+        if seed is None and not any_given and self._series is None:
             # nothing to reproduce on the host: winds (and TI) drawn by the library for the selected envs
             mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
             mask[idt] = 1
@@ -151,7 +165,8 @@ class VecWindFarmEnv:
                 first = self._series[self._series_pos[idt]].cpu().numpy()
                 ws, wd = first[:, 0], first[:, 1]
             else:
-                ws_s, wd_s = (None, None) if given else self.sample_wind_host(seed, ids)
+                ws_s, wd_s = (None, None) if given else self.sample_wind_host(
+                    seed, ids, "wind_speed" not in options, "wind_direction" not in options)
                 ws = np.broadcast_to(np.asarray(options.get("wind_speed", ws_s), dtype=np.float64), ids.shape)
                 wd = np.broadcast_to(np.asarray(options.get("wind_direction", wd_s), dtype=np.float64), ids.shape)
             if self.turbulence_intensity_range is not None:
@@ -186,7 +201,11 @@ class VecWindFarmEnv:
         truncated = out["truncated"].bool()
         self.episode_returns += reward.double()
         self.episode_lengths += 1
-        info = {"power": out["power"], "load": out["load"]}
+        if self.copy_outputs:
+            reward = reward.clone()
+            info = {"power": out["power"].clone(), "load": out["load"].clone()}
+        else:
+            info = {"power": out["power"], "load": out["load"]}
         obs = self._obs(out)
         done_host = self._iters >= self.start_iter + self.max_num_steps
         if done_host.any():
