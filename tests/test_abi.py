@@ -112,3 +112,13 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "floris_oracle" not in text and "env_oracle" not in text, f
+
+
+def test_version_string_carries_the_hash_of_the_sources():
+    """wf_version() names the sources the binary was built from; build() rebuilds on any difference (no GPU needed)."""
+    from wfcrl_b200 import _lib, build
+
+    assert build.library_hash() == build.source_hash()
+    version = _lib.load().wf_version().decode()
+    assert version.startswith("wfcrl_b200 ") and version.endswith("wfcrl_b200-src-sha256:" + build.source_hash())
+    assert _lib.binary_matches_source()

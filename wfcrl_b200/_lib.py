@@ -102,6 +102,11 @@ def load():
     return lib
 
 
+def binary_matches_source() -> bool:
+    """True when the loaded library reports the hash of the sources in the tree (wf_version vs build.source_hash)."""
+    return load().wf_version().decode().endswith("wfcrl_b200-src-sha256:" + _build.source_hash())
+
+
 def check(rc: int):
     if rc != WF_OK:
         raise WfError(f"wfcrl_b200 error {rc}: {load().wf_last_error().decode()}")

@@ -4,6 +4,7 @@ Usage: python -m wfcrl_b200.build [--force]
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -28,12 +29,36 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the wfcrl_b200 CUDA library cannot be built (there is no CPU fallback)")
 
 
+def source_hash() -> str:
+    """SHA-256 (first 16 hex digits) over every source the library is built from: csrc/*.cu, *.cuh, *.h (the generated
+    wf_fast_baked.inc excluded: it is a function of gen_baked.cu + wf_host_const.h) and include/*.h, in name order."""
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    inc = os.path.join(HERE, "..", "include")
+    paths = [os.path.join(CSRC, f) for f in files] + [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+    for path in paths:
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as fp:
+            h.update(fp.read())
+        h.update(b"\0")
+    return h.hexdigest()[:16]
+
+
+def library_hash(path: str = LIB):
+    """The source hash baked into a built library (read from the file, without loading it); None if absent."""
+    try:
+        with open(path, "rb") as fp:
+            blob = fp.read()
+    except OSError:
+        return None
+    tag = b"wfcrl_b200-src-sha256:"
+    k = blob.find(tag)
+    return blob[k + len(tag):k + len(tag) + 16].decode() if k >= 0 else None
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    """True when the library is missing or was built from other sources than the ones in the tree (hash, not mtime)."""
+    return library_hash() != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -48,6 +73,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.remove(gen_exe)
     # step 2: the library
     extra = os.environ.get("WFCRL_NVCC_EXTRA", "").split()  # e.g. -DWF_FAST_MINB=14 for tuning experiments
+    extra.append(f'-DWF_SOURCE_HASH="{source_hash()}"')      # wf_version() reports what the binary was built from
     cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr

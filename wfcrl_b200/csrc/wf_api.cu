@@ -55,6 +55,11 @@ struct WfHandle_t {
     // queued on ITS stream: those record this event, wf_step_host / wf_update_command_host make their streams wait on it
     cudaEvent_t ev_async = nullptr;
     bool ev_pending = false;
+    // staged host path of a strict FP32 handle: compact records of the re-solved envs (device + pinned host), chunk events
+    float *d_fix_rec = nullptr, *h_fix_rec = nullptr;
+    int* h_fix_n = nullptr;
+    int fix_rec_cap = 0;
+    cudaEvent_t ev_chunk[kHostStreams] = {};
     bool fast_uses_vtab = false;  // FP32 step kernel reads the vortex table (off by default: measured slower than direct)
     bool vtab_stale = false;  // some env's vortex-table rows do not match its geometry: launch the kernels that ignore the table
     uint64_t steps_since_wind_update = 1u << 30;  // wf_update_wind rebuilds the vortex table only when it is not called every step
@@ -102,7 +107,12 @@ static cudaError_t launch_geometry(WfHandle h, const uint8_t* d_mask, const doub
 extern "C" {
 
 const char* wf_last_error(void) { return g_err.c_str(); }
-const char* wf_version(void) { return "wfcrl_b200 0.1 (sm_100a)"; }
+#ifndef WF_SOURCE_HASH
+#define WF_SOURCE_HASH "unknown-source-hash"
+#endif
+// "wfcrl_b200 <version> (sm_100a) wfcrl_b200-src-sha256:<first 16 hex digits>": the hash covers csrc/*.cu|cuh|h and include/*.h
+// (wfcrl_b200/build.py: source_hash) -- build() rebuilds when it differs from the tree, smoke() asserts that it matches.
+const char* wf_version(void) { return "wfcrl_b200 0.2 (sm_100a) wfcrl_b200-src-sha256:" WF_SOURCE_HASH; }
 
 int wf_default_config(WfConfig* c) {
     if (!c) return set_err(WF_ERR_INVALID, "cfg is NULL");
@@ -121,6 +131,10 @@ int wf_destroy(WfHandle h) {
     for (cudaStream_t st : h->host_streams)
         if (st) cudaStreamDestroy(st);
     if (h->ev_async) cudaEventDestroy(h->ev_async);
+    for (cudaEvent_t ev : h->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
+    if (h->h_fix_rec) cudaFreeHost(h->h_fix_rec);
+    if (h->h_fix_n) cudaFreeHost(h->h_fix_n);
     delete h;
     return WF_OK;
 }
@@ -214,7 +228,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
         (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) || (rc = dev_alloc(h, &s.amb, (size_t)B)) ||
-        (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)2 * WF_FIX_SLOTS)) ||
+        (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)4 * WF_FIX_SLOTS)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -293,9 +307,22 @@ static WfOutPtrs to_ptrs(const WfStepOut* o) {
     return p;
 }
 
+static bool is_strict_f32(WfHandle h) {
+    return h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F32 && h->model.amb_eps > 0.f;
+}
+
+// FP64 re-solve of the envs flagged by the FP32 launches issued since the previous fix-up (all of them must precede this launch
+// in stream order); d_rec / rec_cap: optional compact copies of the re-solved envs' results (host path)
+static int launch_fixup(WfHandle h, int mode, const WfOutPtrs& out, cudaStream_t st, float* d_rec = nullptr, int rec_cap = 0) {
+    cudaError_t e = wf_launch_fixup64(mode, !h->vtab_stale, h->model, h->fast64, h->st, out, h->model.B, 0, d_rec, rec_cap, st);
+    h->launches += 1;
+    if (e != cudaSuccess) return set_err(WF_ERR_CUDA, std::string("fix-up kernel launch: ") + cudaGetErrorString(e));
+    return WF_OK;
+}
+
 static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float* d_action, const double* d_yaw,
                        const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1,
-                       int slot = WF_FIX_SLOTS - 1) {
+                       bool defer_fixup = false) {
     if (env_count < 0) env_count = h->model.B;
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64)
@@ -303,10 +330,11 @@ static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float*
     else if (h->cfg.kernel == WF_KERNEL_FAST)
     {
         e = wf_launch_step_fast(mode, h->fast_baked, h->fast_uses_vtab && !h->vtab_stale, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
-                                env_count, slot, st);
-        if (e == cudaSuccess && h->model.amb_eps > 0.f) {  // strict FP32: FP64 re-solve of whatever the launch flagged
-            e = wf_launch_fixup64(mode, !h->vtab_stale, h->model, h->fast64, h->st, out, env_begin, env_count, slot, st);
+                                env_count, 0, st);
+        if (e == cudaSuccess && is_strict_f32(h) && !defer_fixup) {  // strict FP32: FP64 re-solve of whatever the launch flagged
             h->launches += 1;
+            h->steps_since_wind_update += 1;
+            return launch_fixup(h, mode, out, st);
         }
     }
     else
@@ -471,6 +499,20 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
     if (ho->freewind) o.freewind = h->d_out.freewind;
     if (ho->truncated) o.truncated = h->d_out.truncated;
     const int nchunk = (B >= 2048) ? WfHandle_t::kHostStreams : 1;
+    // Strict FP32 handle: the chunks' FP32 launches share one fix-up list and ONE FP64 re-solve launch follows the last chunk,
+    // so the chunks' device->host copies overlap the later chunks as before and only the re-solve of the few flagged envs
+    // trails; their results come back as compact records that are scattered into the caller's arrays below.
+    const bool strict = is_strict_f32(h);
+    const int rec_len = WF_FIX_REC_HDR + 8 * (int)T;
+    if (strict && !h->d_fix_rec) {
+        h->fix_rec_cap = (int)(B < 1024 ? B : 1024);
+        TRY(dev_alloc(h, &h->d_fix_rec, (size_t)h->fix_rec_cap * rec_len));
+        if (cudaMallocHost((void**)&h->h_fix_rec, sizeof(float) * (size_t)h->fix_rec_cap * rec_len) != cudaSuccess ||
+            cudaMallocHost((void**)&h->h_fix_n, sizeof(int) * 4) != cudaSuccess)
+            return set_err(WF_ERR_NOMEM, "cudaMallocHost failed");
+        for (int c = 0; c < WfHandle_t::kHostStreams; ++c)
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+    }
     for (int c = 0; c < nchunk; ++c) {
         const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
         cudaStream_t st = h->host_streams[c];
@@ -480,7 +522,8 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
         if (h_yaw)
             CUDA_TRY(cudaMemcpyAsync(h->d_yaw_cmd + b0 * T, h_yaw + b0 * T, sizeof(double) * nb * T, cudaMemcpyHostToDevice, st));
         TRY(launch_step(h, mode, nullptr, h_action ? h->d_action : nullptr, h_yaw ? h->d_yaw_cmd : nullptr, o, st,
-                        (int)b0, (int)nb, c));
+                        (int)b0, (int)nb, /*defer_fixup=*/true));
+        if (strict) CUDA_TRY(cudaEventRecord(h->ev_chunk[c], st));
 #define D2H(field, per_env)                                                                                       \
     if (ho->field) {                                                                                              \
         const size_t off = b0 * (per_env), bytes = nb * (per_env);                                                \
@@ -489,6 +532,47 @@ static int step_host_impl(WfHandle h, int mode, const float* h_action, const dou
         D2H(load, 4 * T * es) D2H(yaw, T * es) D2H(wind_speed, T * es) D2H(wind_direction, T * es) D2H(power, T * es)
         D2H(reward, es) D2H(freewind, 2 * es) D2H(truncated, 1)
 #undef D2H
+    }
+    if (strict) {
+        cudaStream_t fs = h->host_streams[0];
+        for (int c = 1; c < nchunk; ++c) CUDA_TRY(cudaStreamWaitEvent(fs, h->ev_chunk[c], 0));
+        TRY(launch_fixup(h, mode, o, fs, h->d_fix_rec, h->fix_rec_cap));
+        CUDA_TRY(cudaMemcpyAsync(h->h_fix_n, h->st.fix_count, sizeof(int) * 4, cudaMemcpyDeviceToHost, fs));
+        // the first records ride along unconditionally (a typical step re-solves ~1 % of the envs); more only if needed
+        const int eager = h->fix_rec_cap < 160 ? h->fix_rec_cap : 160;
+        CUDA_TRY(cudaMemcpyAsync(h->h_fix_rec, h->d_fix_rec, sizeof(float) * (size_t)eager * rec_len, cudaMemcpyDeviceToHost, fs));
+        for (int c = 0; c < nchunk; ++c) CUDA_TRY(cudaStreamSynchronize(h->host_streams[c]));
+        const int n = h->h_fix_n[2];
+        const int have = n < h->fix_rec_cap ? n : h->fix_rec_cap;
+        if (have > eager) {
+            CUDA_TRY(cudaMemcpyAsync(h->h_fix_rec + (size_t)eager * rec_len, h->d_fix_rec + (size_t)eager * rec_len,
+                                     sizeof(float) * (size_t)(have - eager) * rec_len, cudaMemcpyDeviceToHost, fs));
+            CUDA_TRY(cudaStreamSynchronize(fs));
+        }
+        for (int k = 0; k < have; ++k) {
+            const float* r = h->h_fix_rec + (size_t)k * rec_len;
+            int b;
+            memcpy(&b, r, sizeof(int));
+            const float* pt = r + WF_FIX_REC_HDR;
+            if (ho->reward) ((float*)ho->reward)[b] = r[1];
+            if (ho->freewind) { ((float*)ho->freewind)[2 * b] = r[2]; ((float*)ho->freewind)[2 * b + 1] = r[3]; }
+            if (ho->truncated) ho->truncated[b] = (uint8_t)(r[4] != 0.f);
+            if (ho->yaw) memcpy((float*)ho->yaw + (size_t)b * T, pt, sizeof(float) * T);
+            if (ho->wind_speed) memcpy((float*)ho->wind_speed + (size_t)b * T, pt + T, sizeof(float) * T);
+            if (ho->wind_direction) memcpy((float*)ho->wind_direction + (size_t)b * T, pt + 2 * T, sizeof(float) * T);
+            if (ho->power) memcpy((float*)ho->power + (size_t)b * T, pt + 3 * T, sizeof(float) * T);
+            if (ho->load) memcpy((float*)ho->load + (size_t)b * 4 * T, pt + 4 * T, sizeof(float) * 4 * T);
+        }
+        if (n > have) {  // more re-solved envs than records (never in practice): copy their rows from the device arrays
+#define ROW(field, per_env)                                                                                      \
+    if (ho->field)                                                                                                \
+        CUDA_TRY(cudaMemcpyAsync((char*)ho->field, (char*)h->d_out.field, B * (per_env), cudaMemcpyDeviceToHost, fs));
+            ROW(load, 4 * T * es) ROW(yaw, T * es) ROW(wind_speed, T * es) ROW(wind_direction, T * es) ROW(power, T * es)
+            ROW(reward, es) ROW(freewind, 2 * es) ROW(truncated, 1)
+#undef ROW
+            CUDA_TRY(cudaStreamSynchronize(fs));
+        }
+        return WF_OK;
     }
     for (int c = 0; c < nchunk; ++c) CUDA_TRY(cudaStreamSynchronize(h->host_streams[c]));
     return WF_OK;

@@ -4,7 +4,8 @@
 #include <stdint.h>
 
 #define WF_MAX_TURBINES_K 128  // == WF_MAX_TURBINES of the public header
-#define WF_FIX_SLOTS 8  // concurrent FP32 launches of one handle (wf_step_host chunks) each own a slot of the fix-up counters
+#define WF_FIX_SLOTS 2  // fix-up counter sets (only slot 0 is used: launches of one handle that may overlap share one list)
+#define WF_FIX_REC_HDR 5  // floats ahead of the per-turbine part of a fix-up record (see wf_fixup64_kernel)
 #define WF_NP 9  // 3x3 rotor grid (case.yaml:16), p = 3*j + k with j lateral, k vertical
 
 // Model constants, passed to kernels by value (kernel parameter space = constant bank, broadcast reads).
@@ -38,8 +39,9 @@ struct WfState {
     int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
     uint8_t* amb;       // [B] FP32 kernel: 1 = a discrete decision of this solve was within the guard band of its threshold
                         //     AND could change the result (the env is re-solved by the FP64 kernel), 0 = decisions are safe
-    int* fix_list;      // [B] ids of the envs flagged by the current FP32 launch, written from index env_begin of that launch
-    int* fix_count;     // [2 * WF_FIX_SLOTS] per launch slot: number of flagged envs, number of fix-up CTAs that have left
+    int* fix_list;      // [B] ids of the envs flagged by the FP32 launches since the last fix-up launch (appended atomically)
+    int* fix_count;     // [4 * WF_FIX_SLOTS] per slot: number of flagged envs, number of fix-up CTAs that have left, the
+                        //     number of envs the last fix-up launch re-solved, (pad)
     double* ws;         // [B] free-stream wind speed
     double* wd;         // [B] free-stream wind direction (already % 360)
     double* ws_norm;    // [B] free-stream speed of the PREVIOUS state (reward normalisation, simple_env.py:79)
@@ -137,7 +139,7 @@ cudaError_t wf_launch_step_fast(int mode, bool baked, bool use_vtab, const WfMod
                                 const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                 const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream);
 cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
-                              const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream);
+                              const WfOutPtrs& out, int env_count, int slot, float* d_rec, int rec_cap, cudaStream_t stream);
 cudaError_t wf_step_fast_attributes(bool baked, bool use_vtab, const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                     int* smem);
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,

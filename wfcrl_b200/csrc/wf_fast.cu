@@ -653,7 +653,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const W
     if (any_flag && strict) {
         // the FP64 re-solve (wf_fixup64_kernel, next launch on this stream) redoes this env from the committed yaw state and
         // commits the per-env epilogue state itself
-        if (lane == 0) s.fix_list[env_begin + atomicAdd(&s.fix_count[2 * slot], 1)] = b;
+        if (lane == 0) s.fix_list[atomicAdd(&s.fix_count[4 * slot], 1)] = b;
         return;
     }
     if (lane == 0) {

@@ -34,6 +34,40 @@ __device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- lean double-precision primitives for the solver's critical path ----------------------------------------------------
+// The FP64 kernels are bound by the LATENCY of one warp's chain of dependent double-precision operations, and the library
+// division / sqrt / cbrt (IEEE rounding, full range, special cases) are 15-50 dependent instructions each.  The quantities
+// in the chain are positive, finite and far inside the float range, and the kernels owe 1e-9, not the last bit: seed with the
+// single-precision special-function unit and refine with Newton steps in double (error ~1e-15, a quarter of the instructions).
+__device__ __forceinline__ double rcp64(double b) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)b));
+    double r = (double)rf;
+    r = fma(r, fma(-b, r, 1.0), r);  // 6e-8 -> 4e-15
+    r = fma(r, fma(-b, r, 1.0), r);  // -> rounding
+    return r;
+}
+__device__ __forceinline__ double div64(double a, double b) { return a * rcp64(b); }
+__device__ __forceinline__ double sqrt64(double x) {  // x > 0
+    float rf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+    const double r = (double)rf, h = 0.5 * r;
+    double y = x * r;
+    y = fma(h, fma(-y, y, x), y);  // 1e-7 -> 1e-14
+    y = fma(h, fma(-y, y, x), y);
+    return y;
+}
+__device__ __forceinline__ double sqrt64z(double x) { return x > 1e-30 ? sqrt64(x) : sqrt(x); }  // x >= 0, possibly tiny
+__device__ __forceinline__ double cbrt64(double x) {  // x > 0
+    const double y0 = (double)cbrtf((float)x);
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)(3.0 * y0 * y0)));
+    const double rc = (double)rf;
+    double y = fma(fma(-y0 * y0, y0, x), rc, y0);  // Newton on y^3 = x with a single-precision slope: 1e-7 -> 1e-14
+    y = fma(fma(-y * y, y, x), rc, y);
+    return y;
+}
+
 __device__ __forceinline__ double dclamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double* __restrict__ fp, double x, double left,
@@ -113,7 +147,8 @@ __device__ __forceinline__ void load_row12(const double* __restrict__ p, double*
 template <int W, typename OutT, bool FIX>
 __device__ __forceinline__ void solve_env64(const int b, const int mode, const bool use_vtab, const WfModel& m,
                                             const WfFastConst64& fc, const WfState& s, const float* __restrict__ action,
-                                            const double* __restrict__ yaw_cmd, const WfOutPtrs& out) {
+                                            const double* __restrict__ yaw_cmd, const WfOutPtrs& out,
+                                            float* __restrict__ rec = nullptr) {
     const int T = m.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = 32 * W;
@@ -200,7 +235,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             const double2 vw0 = sm.vw[9 * i + plc];
             vq = vw0.x;
             wwq = vw0.y;
-            const double u = U0p - sqrt(wq);
+            const double u = U0p - sqrt64z(wq);
             su3 = pv ? u * u * u : 0.0;
             sv = pv ? vq : 0.0;
             sw = pv ? wwq : 0.0;
@@ -211,14 +246,14 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 sw += __shfl_xor_sync(0xffffffffu, sw, sft);
             }
         }
-        const double avg = cbrt(su3 / 9.0);
+        const double avg = cbrt64(su3 * (1.0 / 9.0));
         const double ct_raw = dclamp(interp_d(fc, fc.tab_ct, avg, 0.0001, 0.9999), 0.0001, 0.9999);
         const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.yawd[i];
         const double ct = ct_raw * cy;
         // The chain below is the critical path of the FP64 kernels (one warp, dependent double-precision operations): divisions
         // are shared through reciprocals and identities that hold to rounding (1e-16, the tolerance is 1e-9) are used freely.
-        const double rcy = 1.0 / cy, rct = 1.0 / ct;
-        const double a = 0.5 * rcy * (1.0 - sqrt(1.0 - ct * cy));
+        const double rcy = rcp64(cy), rct = rcp64(ct);
+        const double a = 0.5 * rcy * (1.0 - sqrt64(1.0 - ct * cy));
         const double Gtop0 = fc.c_top * ws * ct, Gbot0 = fc.c_bot * ws * ct;
         const double Gwr = fc.c_wr * (a - a * a) * avg;
         const double Gt = sy * cy * Gtop0, Gb = -(sy * cy * Gbot0);
@@ -229,17 +264,17 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double g_deg = -(yd + kDeg * (0.5 * asin(val)));  // minus the effective yaw, degrees
         const double g_rad = g_deg * kRad;
         const double cg = cos(g_rad);
-        const double rcg = 1.0 / cg;
+        const double rcg = rcp64(cg);
 
         // A.6 deflection scalars.  M0 = C0 (2 - C0) = 1 - (1 - C0)^2 = ct.
-        const double sq1ct = sqrt(1.0 - ct);
-        const double sqcg = sqrt(1.0 - ct * cg);
-        const double sz0d = 0.5 * D * sqrt((1.0 + sqcg) / (2.0 * (1.0 + sq1ct)));
+        const double sq1ct = sqrt64(1.0 - ct);
+        const double sqcg = sqrt64(1.0 - ct * cg);
+        const double sz0d = 0.5 * D * sqrt64((1.0 + sqcg) * rcp64(2.0 * (1.0 + sq1ct)));
         const double sy0d = sz0d * cg;
         const double C0 = 1.0 - sq1ct;
         const double E0 = C0 * C0 - fc.e3_112 * C0 + fc.e3_13;
         const double th = fc.dm03 * g_rad * rcg * (1.0 - sqcg);
-        const double sM0 = sqrt(ct);
+        const double sM0 = sqrt64(ct);
         double tan_th;
         if (fabs(th) < 0.35) {
             // always taken for yaw within +-40 deg (|th| <= 0.31).  Maclaurin series of tan up to th^25 -- coefficients
@@ -262,24 +297,24 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         } else {
             tan_th = tan(th);
         }
-        const double Kc = th * E0 * (1.0 / 5.2) * sqrt(sy0d * sz0d * rct);
-        const double A_ln = (1.6 + sM0) / (1.6 - sM0);
-        const double inv_s0d = 1.0 / (sy0d * sz0d);
+        const double Kc = th * E0 * (1.0 / 5.2) * sqrt64(sy0d * sz0d * rct);
+        const double A_ln = (1.6 + sM0) * rcp64(1.6 - sM0);
+        const double inv_s0d = rcp64(sy0d * sz0d);
 
         // ambient + wake-added TI per lateral column: every lane evaluates its own column, the three values travel by shuffle
         const double ta_j = sm.tia[3 * i + j];
-        const double tp_j = sqrt(ta_j * ta_j + I02);
+        const double tp_j = sqrt64(ta_j * ta_j + I02);
         const double tp0 = __shfl_sync(0xffffffffu, tp_j, 0), tp1 = __shfl_sync(0xffffffffu, tp_j, 1),
                      tp2 = __shfl_sync(0xffffffffu, tp_j, 2);
         const double tpre = tp_j;
         const double beta_term = fc.beta2 * (1.0 - sq1ct);
         // x0 = N / Dn and 1 / x0 = Dn / N from one division
         const double x0d_n = D * cg * (1.0 + sqcg), x0d_d = 1.4142135623730951 * (fc.alpha4 * tpre + beta_term);
-        const double x0d_r = 1.0 / (x0d_n * x0d_d);
+        const double x0d_r = rcp64(x0d_n * x0d_d);
         const double x0d = x0d_n * x0d_n * x0d_r, inv_x0d = x0d_d * x0d_d * x0d_r;
         const double kyd = fc.ka * tpre + fc.kb;
         const double delta0 = tan_th * x0d;
-        const double Kck = Kc / kyd;
+        const double Kck = Kc * rcp64(kyd);
 
         // own transverse velocities + yaw-added recovery (in-place TI update)
         const uchar4 ix = sm.idx[i];
@@ -300,14 +335,14 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double kk2 = 3.0 * aI * aI;
         const double v_term = sumV * (1.0 / 9.0), w_term = sumW * (1.0 / 9.0);
         const double k_total = 0.5 * (kk2 + v_term * v_term + w_term * w_term);
-        const double I_mix = sqrt((2.0 / 3.0) * k_total) / avg - tp0;
+        const double I_mix = sqrt64((2.0 / 3.0) * k_total) * rcp64(avg) - tp0;
         const double tq0 = tp0 + 2.0 * I_mix, tq1 = tp1 + 2.0 * I_mix, tq2 = tp2 + 2.0 * I_mix;
         if (tid == 0) sm.tifin[i] = ((tq0 + tq1) + tq2) / 3.0;
         const double tpost = (j == 0) ? tq0 : ((j == 1) ? tq1 : tq2);
 
         // A.8 velocity-model scalars with the updated TI
         const double x0v_n = D * cy * (1.0 + sq1ct), x0v_d = 1.4142135623730951 * (fc.alpha4 * tpost + beta_term);
-        const double x0v_r = 1.0 / (x0v_n * x0v_d);
+        const double x0v_r = rcp64(x0v_n * x0v_d);
         const double x0v = x0v_n * x0v_n * x0v_r, inv_x0v = x0v_d * x0v_d * x0v_r;
         const double kyv = fc.ka * tpost + fc.kb;
         const double sz0v = fc.near_c * (0.5 / 0.501);
@@ -335,13 +370,9 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 // pairs (real a, ground mirror b): (0,2) top, (1,3) bottom, (4,5) wake rotation
                 const double r0 = q + fc.zz2[0][k], r2 = q + fc.zz2[2][k], r1 = q + fc.zz2[1][k], r3 = q + fc.zz2[3][k];
                 const double r4 = q + fc.zz2[4][k], r5 = q + fc.zz2[5][k];
-                // ONE division for the three pair denominators and the downstream decay (products stay < 1e60)
                 const double p02 = r0 * r2, p13 = r1 * r3, p45 = r4 * r5, dd = fc.nu4[k] * dx + eps2;
-                const double P = p02 * p13, Q = p45 * dd;
-                const double inv = 1.0 / (P * Q);
-                const double iP = inv * Q, iQ = inv * P;
-                const double g0 = Gt * (iP * p13), g1 = Gb * (iP * p02), g4 = Gwr * (iQ * dd);
-                const double dec = c_dec * (iQ * p45);
+                const double g0 = Gt * rcp64(p02), g1 = Gb * rcp64(p13), g4 = Gwr * rcp64(p45);
+                const double dec = c_dec * rcp64(dd);
                 const double Xa0 = (1.0 - E * fc.ez[0][k]) * r2, Xb0 = (1.0 - E * fc.ez[2][k]) * r0;
                 const double Xa1 = (1.0 - E * fc.ez[1][k]) * r3, Xb1 = (1.0 - E * fc.ez[3][k]) * r1;
                 const double Xa4 = (1.0 - E * fc.ez[4][k]) * r5, Xb4 = (1.0 - E * fc.ez[5][k]) * r4;
@@ -384,8 +415,8 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             } else {
                 const double dd = dx - x0d;
                 const double sgy = kyd * dd + sy0d, sgz = kyd * dd + sz0d;
-                const double sq = sqrt(sgy * sgz * inv_s0d);
-                const double L = log(A_ln * (1.6 * sq - sM0) / (1.6 * sq + sM0));
+                const double sq = sqrt64(sgy * sgz * inv_s0d);
+                const double L = log(A_ln * (1.6 * sq - sM0) * rcp64(1.6 * sq + sM0));
                 defl = delta0 + Kck * L + lin;
             }
             double base, ek;
@@ -395,11 +426,11 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 const double up = dx * inv_x0v, down = (x0v - dx) * inv_x0v;
                 const double sgy = far ? kyv * dd + sy0v : down * near_s + up * sy0v;
                 const double sgz = far ? kyv * dd + sz0v : down * near_s + up * sz0v;
-                const double inv = 1.0 / (sgy * sgz);  // one division: 1/sgy = sgz*inv, 1/sgz = sgy*inv
+                const double inv = rcp64(sgy * sgz);  // one reciprocal: 1/sgy = sgz*inv, 1/sgz = sgy*inv
                 const double dy = (dyc - defl) * (sgz * inv);
                 const double rz = sgy * inv;
                 const double dcl = dclamp(1.0 - ctc * inv, 0.0, 1.0);
-                base = (1.0 - sqrt(dcl)) * exp(-0.5 * dy * dy);
+                base = (1.0 - sqrt64z(dcl)) * exp(-0.5 * dy * dy);
                 ek = exp(-0.5 * fc.dz2[0] * rz * rz);
             }
             const double be = base * ek;
@@ -417,7 +448,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                               __shfl_sync(0xffffffffu, c, (gb + 2) & 31);
             if (active && c_tot > 0 && t >= gt0_i && t < end15 && fabs(dyc) < fc.two_D) {
                 const double dxp = dx + ((dx <= 0.1) ? 1.0 : 0.0);
-                const double wat = watK * exp(fc.ch_down * log(dxp / D));
+                const double wat = watK * exp(fc.ch_down * log(dxp * fc.inv_D));
                 const double ta = ((double)c_tot / 9.0) * wat;
                 sm.tia[3 * t + j] = fmax(sm.tia[3 * t + j], ta);
             }
@@ -555,6 +586,12 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             OutT* Lp = (OutT*)out.load + 4 * o;
             Lp[0] = (OutT)loads[0]; Lp[1] = (OutT)loads[1]; Lp[2] = (OutT)loads[2]; Lp[3] = (OutT)loads[3];
         }
+        if (FIX && rec) {  // compact copy of the env's results for the host path (wf_step_host scatters it into the caller's arrays)
+            float* r = rec + WF_FIX_REC_HDR;
+            r[orig] = (float)yv; r[T + orig] = (float)wsl; r[2 * T + orig] = (float)wdl; r[3 * T + orig] = (float)p_out;
+            r[4 * T + 4 * orig] = (float)loads[0]; r[4 * T + 4 * orig + 1] = (float)loads[1];
+            r[4 * T + 4 * orig + 2] = (float)loads[2]; r[4 * T + 4 * orig + 3] = (float)loads[3];
+        }
     }
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) {
@@ -568,6 +605,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         double fw0 = ws, fw1 = wd;
         if (mode == WF_MODE_WARMUP) { fw0 = dclamp(fw0, 3.0, 28.0); fw1 = dclamp(fw1, 0.0, 360.0); }
         if (out.freewind) { ((OutT*)out.freewind)[2 * b] = (OutT)fw0; ((OutT*)out.freewind)[2 * b + 1] = (OutT)fw1; }
+        if (FIX && rec) { rec[0] = __int_as_float(b); rec[1] = 0.f; rec[2] = (float)fw0; rec[3] = (float)fw1; rec[4] = (it == m.max_iter) ? 1.f : 0.f; }
         if (mode == WF_MODE_ENV) {
             s.num_moves[b] = nm;
             const double wn = s.ws_norm[b];
@@ -582,6 +620,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             }
             if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((OutT*)out.reward)[b] = (OutT)reward;
+            if (FIX && rec) rec[1] = (float)reward;
             s.ws_norm[b] = ws;
         }
     }
@@ -599,20 +638,26 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
 // Re-solve, in FP64, of the envs an FP32 launch flagged (their ids sit in s.fix_list[env_begin ...], their number in
 // s.fix_count[2 slot]); launched right behind every FP32 step launch of a strict handle, usually with nothing or a handful of
 // envs to do, so it is built for latency: kFixWarps warps per env.  The last CTA to leave re-arms the counters.
-constexpr int kFixWarps = 4;
+#ifndef WF_FIX_WARPS
+#define WF_FIX_WARPS 4
+#endif
+constexpr int kFixWarps = WF_FIX_WARPS;
 __global__ void __launch_bounds__(32 * kFixWarps, 1)
-wf_fixup64_kernel(const int mode, const int env_begin, const int slot, const bool use_vtab, const WfModel m,
-                  const __grid_constant__ WfFastConst64 fc, const WfState s, const WfOutPtrs out) {
-    const int n = *(volatile int*)&s.fix_count[2 * slot];
+wf_fixup64_kernel(const int mode, const int slot, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
+                  const WfState s, const WfOutPtrs out, float* __restrict__ rec, const int rec_cap) {
+    const int n = *(volatile int*)&s.fix_count[4 * slot];
+    const int rec_len = WF_FIX_REC_HDR + 8 * m.T;  // header (env id, reward, freewind x2, truncated) + yaw, ws, wd, power, load x4
     for (int k = blockIdx.x; k < n; k += gridDim.x) {
-        solve_env64<kFixWarps, float, true>(s.fix_list[env_begin + k], mode, use_vtab, m, fc, s, nullptr, nullptr, out);
+        solve_env64<kFixWarps, float, true>(s.fix_list[k], mode, use_vtab, m, fc, s, nullptr, nullptr, out,
+                                            (rec && k < rec_cap) ? rec + (size_t)k * rec_len : nullptr);
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&s.fix_count[2 * slot + 1], 1) == (int)gridDim.x - 1) {
-            s.fix_count[2 * slot] = 0;
-            s.fix_count[2 * slot + 1] = 0;
+        if (atomicAdd(&s.fix_count[4 * slot + 1], 1) == (int)gridDim.x - 1) {
+            s.fix_count[4 * slot + 2] = n;
+            s.fix_count[4 * slot] = 0;
+            s.fix_count[4 * slot + 1] = 0;
         }
     }
 }
@@ -620,7 +665,7 @@ wf_fixup64_kernel(const int mode, const int env_begin, const int slot, const boo
 }  // namespace
 
 cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
-                              const WfOutPtrs& out, int env_begin, int env_count, int slot, cudaStream_t stream) {
+                              const WfOutPtrs& out, int env_count, int slot, float* d_rec, int rec_cap, cudaStream_t stream) {
     const size_t smem = fast64_smem_bytes(m.T);
     static bool configured[64] = {};
     int dev = 0;
@@ -631,7 +676,7 @@ cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const W
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int grid = env_count < 296 ? env_count : 296;  // flagged envs are rare: two CTAs per SM cover any realistic count
-    wf_fixup64_kernel<<<grid, 32 * kFixWarps, smem, stream>>>(mode, env_begin, slot, use_vtab, m, fc, s, out);
+    wf_fixup64_kernel<<<grid, 32 * kFixWarps, smem, stream>>>(mode, slot, use_vtab, m, fc, s, out, d_rec, rec_cap);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@ through the C-ABI (``wf_update_command``), as a batch of one environment.  The b
 """
 from __future__ import annotations
 
+import itertools
 import time
 import warnings
 from abc import ABC
@@ -17,6 +18,18 @@ from typing import List, Union
 import numpy as np
 
 from .environments.data_cases import FarmCase
+
+
+def _load_series(time_series) -> np.ndarray:
+    """Rows [speed, direction, ...] of a wind time series given as an array or as the path of a csv file with a header row."""
+    if isinstance(time_series, str):
+        import pandas as pd
+
+        time_series = pd.read_csv(time_series).values
+    rows = np.asarray(time_series)
+    if rows.ndim != 2 or rows.shape[1] < 2:
+        raise AssertionError("a wind time series holds rows of [speed, direction]")
+    return rows
 
 
 class BaseInterface(ABC):
@@ -110,23 +123,16 @@ class FlorisInterface(BaseInterface):
                    wind_time_series=params["wind_time_series"], xcoords=params["xcoords"], ycoords=params["ycoords"])
 
     def _make_wind_generator(self, wind_speed=None, wind_direction=None, time_series=None):
+        """Iterator of (speed, direction) pairs feeding ``update_wind`` before every solve (reference behaviour,
+        wfcrl/interface.py:503-524): a steady wind repeats forever; a time series (ndarray or csv path, columns speed,
+        direction) is played ONCE, starting from a row drawn with numpy's GLOBAL generator and wrapping around to the row
+        before it -- so ``np.random.seed`` controls the start, and a series shorter than the episode ends in StopIteration,
+        exactly like the reference."""
         if time_series is None:
-            def wind_generator():
-                while True:
-                    yield wind_speed, wind_direction
-        else:
-            if isinstance(time_series, str):
-                import pandas as pd
-
-                time_series = pd.read_csv(time_series).values
-            assert isinstance(time_series, np.ndarray)
-            start = np.random.randint(0, time_series.shape[0])  # random start offset, global RNG (interface.py:517)
-            time_series = np.r_[time_series[start:], time_series[:start]]
-
-            def wind_generator():
-                for ts in time_series:
-                    yield ts
-        return wind_generator()
+            return itertools.repeat((wind_speed, wind_direction))
+        rows = _load_series(time_series)
+        first = np.random.randint(0, rows.shape[0])
+        return iter(np.roll(rows, -first, axis=0))
 
     # -- wind -----------------------------------------------------------------------------------------------------
     @property
@@ -183,10 +189,16 @@ class FlorisInterface(BaseInterface):
         self._powers = out["power"][0].astype(np.float64)  # W in interface mode
         self._num_iter += 1
         if self._logging:
-            with open(self._log_file, "a") as fp:
-                fp.write(f"Sent command YAW {self.get_yaw_command()} - ***********Received Power: "
-                         f"{self.avg_powers()} Wind : {self.avg_wind()}\n")
+            self._append_log()
         return self._num_iter == self.max_iter
+
+    def _append_log(self):
+        """One line per solve in the reference's log format (wfcrl/interface.py:579-585)."""
+        fields = (("Sent command YAW", self.get_yaw_command()), ("***********Received Power:", self.avg_powers()),
+                  ("Wind :", self.avg_wind()))
+        line = f"{fields[0][0]} {fields[0][1]} - {fields[1][0]} {fields[1][1]} {fields[2][0]} {fields[2][1]}\n"
+        with open(self._log_file, "a") as fp:
+            fp.write(line)
 
     # -- measures -------------------------------------------------------------------------------------------------
     def get_yaw_command(self):
