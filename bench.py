@@ -297,7 +297,7 @@ def run_sustained(torch, fb, pool, seconds, B, local, gid0):
             fb.step(pool[k % len(pool)])
         n += 200
         if n % 400 == 0:
-            fb.reset_sampled(None, seed=1, env_id_offset=gid0)
+            fb.reset_sampled(None, seed=1, env_id_offset=gid0)  # (the handle never reaches max_iter here: explicit reset)
         torch.cuda.synchronize()
         if time.time() - t0 >= seconds:
             break
@@ -422,6 +422,9 @@ def run_ours(args):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     fb.reset(ws, wd, host_trig=False)
+    # in-kernel auto-reset: the truncating step zeroes the envs' state itself; one geometry + warm-up launch pair draws the
+    # fresh winds (keyed by (global env id, episode)) and restarts the episodes -- no host round trip
+    fb.set_autoreset(True, seed=0, env_id_offset=gid0)
     steps_in_episode = 0
     returns = torch.zeros(B, dtype=torch.float64, device=dev)
 
@@ -429,8 +432,8 @@ def run_ours(args):
         nonlocal steps_in_episode
         out = fb.step(pool[k % len(pool)])
         steps_in_episode += 1
-        if steps_in_episode >= MAX_NUM_STEPS - 1:  # every env truncates together: device-side reset, new episode
-            fb.reset_sampled(None, seed=0, env_id_offset=gid0)  # fresh winds, keyed by (global env id, episode)
+        if steps_in_episode >= MAX_NUM_STEPS - 1:  # every env truncates together (fixed episode length)
+            fb.autoreset_finish()
             steps_in_episode = 0
         return out
 

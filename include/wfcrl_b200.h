@@ -159,6 +159,20 @@ int wf_reset_sampled(WfHandle h, const uint8_t* d_mask, uint64_t seed, int64_t e
 int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream);
 
 /*
+ * In-kernel auto-reset: the batched counterpart of "env.reset() as soon as the episode truncates" (mdp.py:260-262 behind
+ * simple_env.py:49-56) without a reset launch chain of its own.  Once armed, a wf_step whose env reaches
+ * _num_iter == max_iter ALSO starts that env's next episode inside the step kernel: the wind is drawn as by
+ * wf_reset_sampled (key = seed, counter = (env_id_offset + b, episode index)), yaw / accumulators / counters / shaper state
+ * are zeroed, and the env is marked.  The outputs of that wf_step still hold the FINAL observation of the finished episode.
+ * wf_autoreset_finish then rebuilds the geometry of the marked envs, runs their warm-up solve(s) -- overwriting their rows
+ * of `out` with the start observation -- and clears the marks; with no env marked its launches exit at once, so it may be
+ * called after every step or only when the caller knows an episode ended (episodes have a fixed length).
+ * WF_KERNEL_FAST handles only.  enabled = 0 disarms.
+ */
+int wf_set_autoreset(WfHandle h, int32_t enabled, uint64_t seed, int64_t env_id_offset, double ti_lo, double ti_hi);
+int wf_autoreset_finish(WfHandle h, int32_t warmup_solves, const WfStepOut* out, void* stream);
+
+/*
  * INTERFACE MODE.  Replaces FlorisInterface.update_command(yaw=...) (interface.py:557-586) alone: no constraint, no
  * clipping, no reward.  d_yaw: DEVICE double [B][T] absolute yaw command in degrees, or NULL to keep the current
  * command (update_command() with no argument, mdp.py:262).

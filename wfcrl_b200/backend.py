@@ -138,6 +138,20 @@ class FlorisBatch:
                                              int(warmup_solves), C.byref(self._out_struct), self._stream()))
         return self.out
 
+    def set_autoreset(self, enabled: bool, seed: int = 0, env_id_offset: int = 0,
+                      turbulence_intensity_range: Optional[tuple] = None):
+        """Arm / disarm the in-kernel auto-reset (``wf_set_autoreset``): a step that truncates an env also starts its next
+        episode (wind from the library's counter-based sampler); ``autoreset_finish`` completes it."""
+        lo, hi = turbulence_intensity_range if turbulence_intensity_range is not None else (0.0, 0.0)
+        _lib.check(self.lib.wf_set_autoreset(self.handle, int(bool(enabled)), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                             int(env_id_offset), float(lo), float(hi)))
+
+    def autoreset_finish(self, warmup_solves: int = 1):
+        """Geometry + warm-up solve(s) of the envs the last step(s) reset in-kernel; their output rows become the start
+        observation.  Cheap no-op launches when no env is marked."""
+        _lib.check(self.lib.wf_autoreset_finish(self.handle, int(warmup_solves), C.byref(self._out_struct), self._stream()))
+        return self.out
+
     def reset_masked(self, mask: torch.Tensor, wind_speed: torch.Tensor, wind_direction: torch.Tensor,
                      warmup_solves: int = 1):
         """Device-side reset of the envs where ``mask`` (uint8 [B]) is non-zero; no host round trip."""

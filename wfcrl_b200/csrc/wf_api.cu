@@ -90,8 +90,8 @@ static int mark_async(WfHandle h, cudaStream_t st) {
 
 // rotated + sorted geometry of the selected envs and, unless told otherwise, their vortex-table rows
 static cudaError_t launch_geometry(WfHandle h, const uint8_t* d_mask, const double* d_cs, cudaStream_t st,
-                                   bool build_table = true) {
-    cudaError_t e = wf_launch_geometry(h->model, h->st, d_mask, d_cs, st);
+                                   bool build_table = true, bool autoreset_draw = false) {
+    cudaError_t e = wf_launch_geometry(h->model, h->st, d_mask, d_cs, st, autoreset_draw);
     h->launches += 1;
     if (e == cudaSuccess && build_table && h->st.vtab_ok) {
         e = wf_launch_vortex_table(h->model, h->fast64, h->st, d_mask, st);
@@ -228,7 +228,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
         (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) || (rc = dev_alloc(h, &s.amb, (size_t)B)) ||
-        (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)4 * WF_FIX_SLOTS)) ||
+        (rc = dev_alloc(h, &s.reset_mask, (size_t)B)) || (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)4 * WF_FIX_SLOTS)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -399,6 +399,29 @@ int wf_reset(WfHandle h, const int32_t* ids, int32_t n, const double* ws, const 
         TRY(launch_step(h, WF_MODE_WARMUP, h->d_mask, nullptr, nullptr, to_ptrs(out), st));
     CUDA_TRY(cudaStreamSynchronize(st));  // the handle-owned pinned staging is reusable when this call returns
     return WF_OK;
+}
+
+int wf_set_autoreset(WfHandle h, int32_t enabled, uint64_t seed, int64_t env_id_offset, double ti_lo, double ti_hi) {
+    if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
+    if (enabled && h->cfg.kernel != WF_KERNEL_FAST)
+        return set_err(WF_ERR_INVALID, "in-kernel auto-reset needs the warp-per-env kernels (WF_KERNEL_FAST)");
+    if (env_id_offset < 0) return set_err(WF_ERR_INVALID, "env_id_offset must be >= 0");
+    if (ti_hi > ti_lo && !(ti_lo > 0.0)) return set_err(WF_ERR_INVALID, "turbulence-intensity range must be positive");
+    WfModel& m = h->model;
+    m.autoreset = enabled ? 1 : 0;
+    m.ar_seed = seed; m.ar_offset = env_id_offset; m.ar_ti_lo = ti_lo; m.ar_ti_hi = ti_hi;
+    return WF_OK;
+}
+
+int wf_autoreset_finish(WfHandle h, int32_t warmup, const WfStepOut* out, void* stream) {
+    if (!h) return set_err(WF_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* mask = h->st.reset_mask;
+    CUDA_TRY(launch_geometry(h, mask, nullptr, st, true, /*autoreset_draw=*/true));
+    for (int k = 0; k < warmup; ++k) TRY(launch_step(h, WF_MODE_WARMUP, mask, nullptr, nullptr, to_ptrs(out), st));
+    CUDA_TRY(cudaMemsetAsync(h->st.reset_mask, 0, (size_t)h->model.B, st));
+    return mark_async(h, st);
 }
 
 int wf_step(WfHandle h, const float* d_action, const WfStepOut* out, void* stream) {

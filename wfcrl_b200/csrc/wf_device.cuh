@@ -14,6 +14,10 @@ struct WfModel {
     int max_iter, continuous, multi_agent, shaper, table_len;
     float yaw_lo_f, yaw_hi_f, yaw_step_f;  // float32 bounds exactly as gymnasium Box stores them (mdp.py:111-116,143-144)
     float rate_f, dt_f;
+    int autoreset;                 // step kernels reset an env themselves when its step truncates (wf_set_autoreset)
+    unsigned long long ar_seed;    //   key of the counter-based wind sampler
+    long long ar_offset;           //   global id of env 0 (the sampler's counter word)
+    double ar_ti_lo, ar_ti_hi;     //   ambient-TI range drawn at reset (ti_hi <= ti_lo: keep the current value)
     float amb_eps;                 // relative half-width of the guard band around the 0.05 m/s overlap threshold (FP32 kernel)
     double load_coef, shaper_reference;
     double rho, ref_rho, shear, D, HH, TSR, pP;
@@ -39,6 +43,7 @@ struct WfState {
     int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
     uint8_t* amb;       // [B] FP32 kernel: 1 = a discrete decision of this solve was within the guard band of its threshold
                         //     AND could change the result (the env is re-solved by the FP64 kernel), 0 = decisions are safe
+    uint8_t* reset_mask;// [B] 1 = the env was reset inside a step kernel and still needs its geometry + warm-up solve
     int* fix_list;      // [B] ids of the envs flagged by the FP32 launches since the last fix-up launch (appended atomically)
     int* fix_count;     // [4 * WF_FIX_SLOTS] per slot: number of flagged envs, number of fix-up CTAs that have left, the
                         //     number of envs the last fix-up launch re-solved, (pad)
@@ -121,7 +126,7 @@ enum WfMode { WF_MODE_INTERFACE = 0, WF_MODE_ENV = 1, WF_MODE_WARMUP = 2 };
 
 // launchers implemented in wf_kernels.cu
 cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_cs_override,
-                               cudaStream_t stream);
+                               cudaStream_t stream, bool autoreset_draw = false);
 cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, const WfState& s, const uint8_t* d_mask,
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
                                  int env_begin, int env_count, cudaStream_t stream);

@@ -28,6 +28,7 @@
 // Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
 // wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
 #include "wf_device.cuh"
+#include "wf_reset_device.cuh"
 #include "wf_fast_baked.inc"
 
 #include <stdlib.h>
@@ -167,7 +168,7 @@ struct wf_true_tag { static constexpr bool value = true; };
 struct wf_false_tag { static constexpr bool value = false; };
 
 template <bool BAKED, bool VTAB>
-__global__ void __launch_bounds__(32, VTAB ? 16 : WF_FAST_MINB)
+__global__ void __launch_bounds__(32, (VTAB || BAKED) ? 16 : WF_FAST_MINB)
 wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const WfModel m, const __grid_constant__ WfFastConst fc,
                     const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                     const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
@@ -656,8 +657,9 @@ wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const W
         if (lane == 0) s.fix_list[atomicAdd(&s.fix_count[4 * slot], 1)] = b;
         return;
     }
+    int it = 0;
     if (lane == 0) {
-        const int it = s.num_iter[b] + 1;
+        it = s.num_iter[b] + 1;
         s.num_iter[b] = it;
         if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
         float fw0 = ws, fw1 = wd;
@@ -680,6 +682,12 @@ wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const W
             if (out.reward) ((float*)out.reward)[b] = reward;
             s.ws_norm[b] = ws_d;
         }
+    }
+    // in-kernel auto-reset (wf_set_autoreset): the step that truncates also starts the env's next episode -- zero yaw /
+    // accumulators / counters -- and marks the env for wf_autoreset_finish (wind draw + geometry + warm-up solve); the outputs written above remain the FINAL observation of the finished episode
+    if (mode == WF_MODE_ENV && m.autoreset && __shfl_sync(0xffffffffu, (int)(it == m.max_iter), 0)) {
+        for (int tt = lane; tt < T; tt += 32) { s.yaw[row + tt] = 0.0; s.acc[row + tt] = 0.f; s.acc_prev[row + tt] = 0.f; }
+        if (lane == 0) wfreset::autoreset_mark(s, b);
     }
 }
 

@@ -15,6 +15,7 @@
 // Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
 // wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
 #include "wf_device.cuh"
+#include "wf_reset_device.cuh"
 
 #include <math.h>
 
@@ -246,7 +247,11 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 sw += __shfl_xor_sync(0xffffffffu, sw, sft);
             }
         }
+#ifdef WF_DBG_SKIP_CBRT  // timing experiment only
+        const double avg = 8.0 + 1e-9 * su3;
+#else
         const double avg = cbrt64(su3 * (1.0 / 9.0));
+#endif
         const double ct_raw = dclamp(interp_d(fc, fc.tab_ct, avg, 0.0001, 0.9999), 0.0001, 0.9999);
         const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.yawd[i];
         const double ct = ct_raw * cy;
@@ -261,9 +266,15 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         // A.5 secondary steering through the per-model grid integrals (the denominator is (c_top a_top - c_bot a_bot) ws ct)
         double val = 2.0 * (sv * (1.0 / 9.0) - Gwr * fc.a_core) * (rct * fc.inv_ss_den) * rws;
         val = dclamp(val, -1.0, 1.0);
+#ifdef WF_DBG_SKIP_TRIG  // timing experiment only
+        const double g_deg = -(yd + kDeg * (0.5 * val));
+        const double g_rad = g_deg * kRad;
+        const double cg = 1.0 - 0.5 * g_rad * g_rad;
+#else
         const double g_deg = -(yd + kDeg * (0.5 * asin(val)));  // minus the effective yaw, degrees
         const double g_rad = g_deg * kRad;
         const double cg = cos(g_rad);
+#endif
         const double rcg = rcp64(cg);
 
         // A.6 deflection scalars.  M0 = C0 (2 - C0) = 1 - (1 - C0)^2 = ct.
@@ -349,7 +360,11 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double sy0v = sz0v * cy;
         const double near_s = fc.near_c * sM0;
         const double ctc = ct * cy * fc.d2_8;
+#ifdef WF_DBG_SKIP_POW  // timing experiment only
+        const double watK = fc.ch_const * a * I0p;
+#else
         const double watK = fc.ch_const * exp(fc.ch_ai * log(a)) * I0p;  // a^ai (pow(): 3x the instructions, same to 1e-15)
+#endif
 
         const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
         const double x_i = sm.xi[i], y_i = sm.yi[i];
@@ -509,11 +524,15 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 const double dx = sm.xs[t] - x_i;
                 const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
                 const bool tab = vrow && t >= t_hi;
+#ifndef WF_DBG_SKIP_V  // timing experiment only
                 if (__any_sync(0xffffffffu, active && !tab)) v_direct(t, dx, dyc, active && !tab);
                 if (tab) v_table(t, active);
+#endif
                 const bool need = active && (t >= near_i) && (fabs(dyc) < reach(dx));
                 const unsigned nb = __ballot_sync(0xffffffffu, need);
+#ifndef WF_DBG_SKIP_D  // timing experiment only
                 if (nb) d_apply(t, dx, dyc, active && (((nb >> (3 * g)) & 7u) != 0u));
+#endif
             }
             __syncthreads();
         }
@@ -598,8 +617,9 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         rsum_p += __shfl_xor_sync(0xffffffffu, rsum_p, sft);
         rsum_l += __shfl_xor_sync(0xffffffffu, rsum_l, sft);
     }
+    int it = 0;
     if (lane == 0) {
-        const int it = s.num_iter[b] + 1;
+        it = s.num_iter[b] + 1;
         s.num_iter[b] = it;
         if (out.truncated) out.truncated[b] = (uint8_t)(it == m.max_iter);
         double fw0 = ws, fw1 = wd;
@@ -624,6 +644,12 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             s.ws_norm[b] = ws;
         }
     }
+    // in-kernel auto-reset (see wf_fast.cu): the truncating step starts the env's next episode and marks it for
+    // wf_autoreset_finish; the outputs above remain the final observation
+    if (mode == WF_MODE_ENV && m.autoreset && __shfl_sync(0xffffffffu, (int)(it == m.max_iter), 0)) {
+        for (int tt = lane; tt < T; tt += 32) { s.yaw[row + tt] = 0.0; s.acc[row + tt] = 0.f; s.acc_prev[row + tt] = 0.f; }
+        if (lane == 0) wfreset::autoreset_mark(s, b);
+    }
 }
 
 __global__ void __launch_bounds__(32, 4)
@@ -637,19 +663,16 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
 
 // Re-solve, in FP64, of the envs an FP32 launch flagged (their ids sit in s.fix_list[env_begin ...], their number in
 // s.fix_count[2 slot]); launched right behind every FP32 step launch of a strict handle, usually with nothing or a handful of
-// envs to do, so it is built for latency: kFixWarps warps per env.  The last CTA to leave re-arms the counters.
-#ifndef WF_FIX_WARPS
-#define WF_FIX_WARPS 4
-#endif
-constexpr int kFixWarps = WF_FIX_WARPS;
-__global__ void __launch_bounds__(32 * kFixWarps, 1)
+// envs to do, so it is built for latency: W warps per env.  The last CTA to leave re-arms the counters.
+template <int W>
+__global__ void __launch_bounds__(32 * W, 1)
 wf_fixup64_kernel(const int mode, const int slot, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
                   const WfState s, const WfOutPtrs out, float* __restrict__ rec, const int rec_cap) {
     const int n = *(volatile int*)&s.fix_count[4 * slot];
     const int rec_len = WF_FIX_REC_HDR + 8 * m.T;  // header (env id, reward, freewind x2, truncated) + yaw, ws, wd, power, load x4
     for (int k = blockIdx.x; k < n; k += gridDim.x) {
-        solve_env64<kFixWarps, float, true>(s.fix_list[k], mode, use_vtab, m, fc, s, nullptr, nullptr, out,
-                                            (rec && k < rec_cap) ? rec + (size_t)k * rec_len : nullptr);
+        solve_env64<W, float, true>(s.fix_list[k], mode, use_vtab, m, fc, s, nullptr, nullptr, out,
+                                    (rec && k < rec_cap) ? rec + (size_t)k * rec_len : nullptr);
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -664,20 +687,30 @@ wf_fixup64_kernel(const int mode, const int slot, const bool use_vtab, const WfM
 
 }  // namespace
 
-cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
-                              const WfOutPtrs& out, int env_count, int slot, float* d_rec, int rec_cap, cudaStream_t stream) {
-    const size_t smem = fast64_smem_bytes(m.T);
+template <int W>
+static cudaError_t launch_fixup_t(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                                  const WfOutPtrs& out, int grid, int slot, float* d_rec, int rec_cap, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(wf_fixup64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wf_fixup64_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    const int grid = env_count < 296 ? env_count : 296;  // flagged envs are rare: two CTAs per SM cover any realistic count
-    wf_fixup64_kernel<<<grid, 32 * kFixWarps, smem, stream>>>(mode, slot, use_vtab, m, fc, s, out, d_rec, rec_cap);
+    wf_fixup64_kernel<W><<<grid, 32 * W, fast64_smem_bytes(m.T), stream>>>(mode, slot, use_vtab, m, fc, s, out, d_rec, rec_cap);
     return cudaGetLastError();
+}
+
+cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
+                              const WfOutPtrs& out, int env_count, int slot, float* d_rec, int rec_cap, cudaStream_t stream) {
+    // The launch is latency-bound (a handful of envs, each a sequential sweep over its turbines): 8 warps per env cover 80
+    // targets in ONE fused pass per source; 4 warps (two resident CTAs per SM instead of one) when the farm is small enough
+    // for one pass anyway or the batch is large enough for the flagged envs to outnumber the SMs.
+    const bool wide = m.T > 40 && env_count <= 12288;
+    const int grid = env_count < (wide ? 148 : 296) ? env_count : (wide ? 148 : 296);
+    return wide ? launch_fixup_t<8>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream)
+                : launch_fixup_t<4>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
 }
 
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,

@@ -10,6 +10,7 @@
 // wfcrl/simulators/floris/inputs/template/case.yaml) -- reference call sites wfcrl/interface.py:557-586, 622-648;
 // env semantics wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py.
 #include "wf_device.cuh"
+#include "wf_reset_device.cuh"
 
 #include <math.h>
 
@@ -60,13 +61,6 @@ template <typename R> __device__ __forceinline__ R sum9(const R* p) {
     return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
 }
 template <typename R> __device__ __forceinline__ R mean9(const R* p) { return M<R>::div(sum9(p), R(9)); }
-
-// python float % for a positive modulus
-__device__ __forceinline__ double fmod_py(double a, double m) {
-    double r = fmod(a, m);
-    if (r != 0.0 && r < 0.0) r += m;
-    return r;
-}
 
 // np.interp + scipy interp1d fill values on the turbine table (table lives in global memory, L1-resident)
 __device__ __forceinline__ double interp_table(double x, const double* __restrict__ xp, const double* __restrict__ fp,
@@ -154,7 +148,7 @@ template <> struct Lat<float> {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WF_MAX_TURBINES_K)
 wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
-                   const double* __restrict__ cs_override) {
+                   const double* __restrict__ cs_override, const int autoreset_draw) {
     const int b = blockIdx.x;
     if (mask && !mask[b]) return;
     const int T = m.T;
@@ -162,13 +156,14 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
     __shared__ double xr[WF_MAX_TURBINES_K], yr[WF_MAX_TURBINES_K], xsrt[WF_MAX_TURBINES_K];
     __shared__ double cs[2];
     if (t == 0) {
+        if (autoreset_draw) wfreset::autoreset_wind(m, s, b);  // second half of an in-kernel auto-reset: the new episode's wind
         double c, sn;
         if (cs_override) {
             c = cs_override[2 * b];
             sn = cs_override[2 * b + 1];
         } else {
             const double wd = s.wd[b];
-            const double dev = fmod_py(fmod_py(wd - 270.0, 360.0) + 360.0, 360.0);
+            const double dev = wfreset::fmod_py(wfreset::fmod_py(wd - 270.0, 360.0) + 360.0, 360.0);
             const double rad = dev * (kPi / 180.0);
             c = cos(rad);
             sn = sin(rad);
@@ -305,52 +300,18 @@ __global__ void wf_set_wind_kernel(const WfModel m, const WfState s, const uint8
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= m.B || (mask && !mask[b])) return;
     s.ws[b] = ws[b];
-    s.wd[b] = fmod_py(wd[b], 360.0);
+    s.wd[b] = wfreset::fmod_py(wd[b], 360.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// reset sampler: the reference's reset distribution (mdp.py:242-258) from a counter-based generator
+// reset kernels (sampler and state: wf_reset_device.cuh)
 // ---------------------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11).  key = the user's 64-bit seed, counter = (global env id lo, hi, episode index
-// of that env, draw index): every (env, episode) owns its words no matter how the envs are sharded over handles or
-// GPUs, so 1/2/4/8-GPU runs reset to identical winds.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-// 53-bit uniform in [0, 1) from two words (the construction numpy's Generator.random uses on 64-bit output)
-__device__ __forceinline__ double u53(unsigned a, unsigned b) {
-    return (double)(((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6)) * (1.0 / 9007199254740992.0);
-}
-
 __global__ void wf_sample_reset_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__ mask,
                                        const unsigned long long seed, const long long env_id_offset, const double ti_lo,
                                        const double ti_hi, double* __restrict__ ws, double* __restrict__ wd) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= m.B || (mask && !mask[b])) return;
-    const unsigned long long gid = (unsigned long long)(env_id_offset + b);
-    const unsigned ep = (unsigned)s.episode[b];
-    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
-    const uint4 r0 = philox4x32_10(make_uint4((unsigned)gid, (unsigned)(gid >> 32), ep, 0u), key);
-    const uint4 r1 = philox4x32_10(make_uint4((unsigned)gid, (unsigned)(gid >> 32), ep, 1u), key);
-    // wind speed = clip(8 * Weibull(k = 8), 3, 28) by inversion (mdp.py:242-247): Weibull(k) = Exp(1)^(1/k)
-    const double e1 = -log1p(-u53(r0.x, r0.y));
-    ws[b] = fmin(fmax(8.0 * pow(e1, 0.125), 3.0), 28.0);
-    // wind direction = clip(N(270, 20) % 360, 0, 360) (mdp.py:253-258), Box-Muller on two uniforms
-    const double rad = sqrt(-2.0 * log1p(-u53(r0.z, r0.w)));
-    const double z = rad * cospi(2.0 * u53(r1.x, r1.y));
-    wd[b] = fmin(fmax(fmod_py(270.0 + 20.0 * z, 360.0), 0.0), 360.0);
-    // extension (BASELINE.json configs[2]): ambient TI ~ U(ti_lo, ti_hi) per episode; the reference fixes it (case.yaml:33)
-    if (ti_hi > ti_lo) s.ti_amb[b] = ti_lo + (ti_hi - ti_lo) * u53(r1.z, r1.w);
-    s.episode[b] = (int)(ep + 1u);
+    wfreset::sample_wind(s, b, seed, env_id_offset, ti_lo, ti_hi, &ws[b], &wd[b]);
 }
 
 // reset per-env scalars/accumulators for masked envs
@@ -366,15 +327,8 @@ __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const ui
         s.acc_prev[o] = 0.f;
     }
     if (threadIdx.x == 0) {
-        const double w = ws[b];
-        s.ws[b] = w;
-        s.wd[b] = fmod_py(wd[b], 360.0);  // interface.py:664
-        s.ws_norm[b] = fmin(fmax(w, 3.0), 28.0);  // start_state is clipped to the observation space (mdp.py:266)
-        s.num_iter[b] = 0;
-        s.num_moves[b] = 0;
-        // WindFarmEnv.reset calls reward_shaper.reset(), and StepPercentage.reset() puts its reference back to 0.0 whatever
-        // the constructor argument was (rewards.py:45-46): the first shaped reward of every episode is 0
-        s.shaper_ref[b] = 0.0;
+        wfreset::reset_scalars(s, b, ws[b], wd[b]);
+        s.reset_mask[b] = 0;  // an explicit reset supersedes a pending in-kernel auto-reset of this env
     }
 }
 
@@ -802,8 +756,8 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
 static inline int round_up_warp(int n) { return (n + 31) / 32 * 32; }
 
 cudaError_t wf_launch_geometry(const WfModel& m, const WfState& s, const uint8_t* d_mask, const double* d_cs_override,
-                               cudaStream_t stream) {
-    wf_geometry_kernel<<<m.B, round_up_warp(m.T), 0, stream>>>(m, s, d_mask, d_cs_override);
+                               cudaStream_t stream, bool autoreset_draw) {
+    wf_geometry_kernel<<<m.B, round_up_warp(m.T), 0, stream>>>(m, s, d_mask, d_cs_override, autoreset_draw ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -93,7 +93,9 @@ class VecWindFarmEnv:
         self._gen = torch.Generator(device=self.device)  # time-series start offsets of in-loop resets only
         self._gen.manual_seed(0x5EED + self.env_id_offset)
         self._seed = int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFFFFFF  # replaced by reset(seed=...)
-        self._iters = np.zeros(self.num_envs, dtype=np.int64)  # host mirror of FlorisInterface._num_iter
+        # Episodes have a fixed length, so the host knows WHEN envs truncate without looking at the device: one countdown per
+        # cohort of envs that were reset together (a handful of python ints, no per-env mirror)
+        self._countdowns = []
         self._series = None
         if wind_time_series is not None:
             if isinstance(wind_time_series, str):  # csv path: first column speed, second direction (interface.py:473-474, 514)
@@ -106,11 +108,34 @@ class VecWindFarmEnv:
             self._series_pos = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         # extension (BASELINE.json configs[2]): ambient TI sampled per env at reset, U(lo, hi); the reference fixes 0.06
         self.turbulence_intensity_range = turbulence_intensity_range
+        self._arm_autoreset()
         self._zeros_bool = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.episode_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         self.finished_returns, self.finished_lengths = [], []
         self._needs_reset = True
+
+    def _arm_autoreset(self):
+        """In-kernel auto-reset (wf_set_autoreset): the truncating step itself zeroes the env's state and marks it; one
+        geometry + warm-up launch pair (``autoreset_finish``) completes the reset.  Time-series mode restarts the series at
+        a host-drawn row and keeps the explicit reset path."""
+        self._fused_autoreset = bool(self.auto_reset and self._series is None)
+        self.backend.set_autoreset(self._fused_autoreset, self._seed, self.env_id_offset, self.turbulence_intensity_range)
+
+    def _tick(self) -> bool:
+        """Advance the cohort countdowns by one step; True when some cohort's episode ends at this step."""
+        fired = False
+        nxt = set()
+        for c in self._countdowns:
+            c -= 1
+            if c == 0:
+                fired = True
+                if self.auto_reset:
+                    nxt.add(self.max_num_steps - 1)
+            else:
+                nxt.add(c)
+        self._countdowns = sorted(nxt)
+        return fired
 
     # -- wind sampling ------------------------------------------------------------------------------------------
     def sample_wind_host(self, seed: Optional[int], env_ids: np.ndarray, need_speed: bool = True,
@@ -177,7 +202,10 @@ class VecWindFarmEnv:
                 self.backend.set_turbulence_intensity(torch.as_tensor(ti, device=self.device))
             out = self.backend.reset(ws, wd, env_ids=ids.astype(np.int32), host_trig=self.exact_host_trig,
                                      warmup_solves=warm)
-        self._iters[ids] = warm
+        self._arm_autoreset()  # (re)arm with the current seed: in-loop resets are keyed by it
+        if len(ids) == self.num_envs:
+            self._countdowns = []
+        self._countdowns = sorted(set(self._countdowns) | {self.max_num_steps - 1})
         self.episode_returns[idt] = 0
         self.episode_lengths[idt] = 0
         self._needs_reset = False
@@ -196,7 +224,6 @@ class VecWindFarmEnv:
             row = self._series[self._series_pos]
             self.backend.update_wind(row[:, 0].contiguous(), row[:, 1].contiguous(), host_trig=self.exact_host_trig)
         out = self.backend.step(action)
-        self._iters += 1
         reward = out["reward"]
         truncated = out["truncated"].bool()
         self.episode_returns += reward.double()
@@ -207,9 +234,7 @@ class VecWindFarmEnv:
         else:
             info = {"power": out["power"], "load": out["load"]}
         obs = self._obs(out)
-        done_host = self._iters >= self.start_iter + self.max_num_steps
-        if done_host.any():
-            mask = out["truncated"]
+        if self._tick():
             self.finished_returns.append(self.episode_returns[truncated].clone())
             self.finished_lengths.append(self.episode_lengths[truncated].clone())
             if self.auto_reset:
@@ -218,19 +243,20 @@ class VecWindFarmEnv:
                 info["final_info"] = {"power": out["power"].clone(), "load": out["load"].clone()}
                 truncated = truncated.clone()
                 reward = reward.clone()
-                if self._series is not None:  # the wind generator restarts at a random row (interface.py:517)
+                if self._fused_autoreset:
+                    # the step kernel has already reset the truncated envs' state and marked them: wind draw + geometry +
+                    # warm-up solve of the marked envs, no host round trip
+                    out = self.backend.autoreset_finish(self.start_iter + 1)
+                else:  # time series: the wind generator restarts at a random row (interface.py:517)
+                    mask = out["truncated"]
                     start = torch.randint(0, self._series.shape[0], (self.num_envs,), device=self.device, generator=self._gen)
                     self._series_pos = torch.where(truncated, start, self._series_pos)
                     row = self._series[self._series_pos]
                     out = self.backend.reset_masked(mask.clone(), row[:, 0].contiguous(), row[:, 1].contiguous(),
                                                     warmup_solves=self.start_iter + 1)
-                else:
-                    out = self.backend.reset_sampled(mask.clone(), self._seed, self.env_id_offset, self.start_iter + 1,
-                                                     self.turbulence_intensity_range)
                 obs = self._obs(out)
                 self.episode_returns[truncated] = 0
                 self.episode_lengths[truncated] = 0
-                self._iters[done_host] = self.start_iter + 1
         self.last_info = info  # joint (un-split) info of this step, incl. final_observation on auto-reset steps
         return obs, reward, self._zeros_bool, truncated, info
 
