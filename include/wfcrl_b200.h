@@ -79,7 +79,8 @@ typedef struct WfConfig {
     /* turbine (nrel_5MW) */
     double rotor_diameter, hub_height, tsr, pP, pT, generator_efficiency, ref_density_cp_ct;
     int32_t table_len;
-    int32_t reserved1;
+    int32_t turbine_grid_points; /* rotor grid points per side (case.yaml:16): 0 or 3 = the template's 3x3 grid; 5 = 5x5, evaluated
+                                    by the WF_KERNEL_BASIC kernels only (generalisation knob) */
     double table_ws[WF_TABLE_MAX], table_cp[WF_TABLE_MAX], table_ct[WF_TABLE_MAX];
 } WfConfig;
 

@@ -52,11 +52,18 @@ def test_reference_template_parses_to_the_library_defaults():
     assert (parsed["wind_speed"], parsed["wind_direction"]) == (8.0, 270.0)
 
 
+def test_five_point_grid_is_accepted_and_routed():
+    case = copy.deepcopy(CASE)
+    case["solver"]["turbine_grid_points"] = 5
+    assert parse_floris_config(case)["overrides"]["turbine_grid_points"] == 5   # FlorisInterface then picks the basic kernels
+    assert parse_floris_config(CASE)["overrides"]["turbine_grid_points"] == 3
+
+
 @pytest.mark.parametrize("mutate,needle", [
     (lambda c: c["wake"]["model_strings"].__setitem__("velocity_model", "jensen"), "velocity_model"),
     (lambda c: c["wake"]["model_strings"].__setitem__("deflection_model", "jimenez"), "deflection_model"),
     (lambda c: c["wake"].__setitem__("enable_secondary_steering", False), "enable_secondary_steering"),
-    (lambda c: c["solver"].__setitem__("turbine_grid_points", 5), "turbine_grid_points"),
+    (lambda c: c["solver"].__setitem__("turbine_grid_points", 7), "turbine_grid_points"),
     (lambda c: c["farm"].__setitem__("turbine_type", ["iea_10MW"]), "turbine_type"),
     (lambda c: c["wake"]["wake_velocity_parameters"]["gauss"].__setitem__("ka", 0.5), "share ka"),
     (lambda c: c["flow_field"].__setitem__("wind_speeds", [8.0, 9.0]), "exactly one wind speed"),

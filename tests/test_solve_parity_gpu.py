@@ -136,3 +136,42 @@ def test_sampled_turbulence_intensity_per_env(cuda_device, precision, kernel):
         assert rel_err(tiout[b], ref.ti, 1e-3) <= max(tol, 1e-9)
     assert np.allclose(fb.get_state("ti_ambient"), ti)
     fb.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_five_by_five_rotor_grid_basic_kernel(cuda_device, precision):
+    """SURVEY 8f row 4 (case.yaml:16 `turbine_grid_points`): a 5x5 rotor grid through the basic kernels against the numpy
+    oracle (which is generic in the grid size; the C oracle and the tuned kernels are 3x3 only and must refuse)."""
+    import torch
+
+    from oracle import floris_oracle
+    from wfcrl_b200 import _lib
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb6_Row2_")
+    B, T = 6, len(lx)
+    ws, wd = sample_winds(B, 31, tie_every=3)
+    yaw = np.random.default_rng(32).uniform(-30, 30, (B, T)).astype(np.float32).astype(np.float64)
+    fb = FlorisBatch(lx, ly, B, precision=precision, kernel="basic", max_iter=10, config_overrides={"turbine_grid_points": 5})
+    fb.reset(ws, wd, host_trig=True, warmup_solves=0)
+    out = fb.update_command(torch.as_tensor(yaw, device="cuda"))
+    torch.cuda.synchronize()
+    got = {k: v.double().cpu().numpy() for k, v in out.items()}
+    order = fb.get_state("order")
+    fb.close()
+    tol = 1e-9 if precision == "f64" else 1e-4
+    floris_oracle.CASE["grid_points"] = 5
+    try:
+        for b in range(B):
+            c, s = host_trig(wd[b])
+            ref = floris_oracle.solve(lx, ly, ws[b], wd[b], yaw[b], cs=(c, s))
+            assert np.array_equal(order[b], ref.order)
+            assert rel_err(got["power"][b], ref.power_W, 1.0) <= tol, (b, precision)
+            assert rel_err(got["wind_speed"][b], ref.ws_local, 1e-3) <= tol
+            assert rel_err(got["wind_direction"][b], ref.wd_local, 1.0) <= tol
+            assert rel_err(got["load"][b, :, 0] / 1e7, ref.ti, 1e-3) <= max(tol, 1e-9)
+            assert rel_err(got["load"][b, :, 1] / 1e7, ref.std_u, 1e-3) <= (tol if precision == "f64" else 2e-3)
+    finally:
+        floris_oracle.CASE["grid_points"] = 3
+    with pytest.raises(_lib.WfError, match="WF_KERNEL_BASIC"):
+        FlorisBatch(lx, ly, B, precision=precision, kernel="fast", config_overrides={"turbine_grid_points": 5})

@@ -1,5 +1,6 @@
 """Large randomized parity sweep of the tuned kernels against the C oracle (evidence for DESIGN.md section 3):
-error distribution of per-turbine power / reward and the rate of discrete flips (overlap-count threshold) in FP32."""
+error distribution of per-turbine power (1 W floor) for the FP64 kernel, the strict FP32 mode (default: flagged solves redone
+in FP64) and the relaxed FP32 mode (raw FP32, shows the discrete flips the strict mode removes)."""
 import json
 import os
 import sys
@@ -26,8 +27,8 @@ for name, B in (("HornsRev1_", 32768), ("Turb32_Row5_", 32768), ("Ablaincourt_",
     t0 = time.time()
     ref = c_oracle.solve_batch(lx, ly, ws, wd, yaw, cs=cs)
     t_ref = time.time() - t0
-    for precision in ("f32", "f64"):
-        fb = FlorisBatch(lx, ly, B, precision=precision, kernel="fast", max_iter=10)
+    for precision, strict in (("f32", True), ("f32", False), ("f64", True)):
+        fb = FlorisBatch(lx, ly, B, precision=precision[:3], kernel="fast", max_iter=10, strict=strict)
         fb.reset(ws, wd, host_trig=True, warmup_solves=0)
         o = fb.update_command(torch.as_tensor(yaw, device="cuda"))
         torch.cuda.synchronize()
@@ -45,9 +46,11 @@ for name, B in (("HornsRev1_", 32768), ("Turb32_Row5_", 32768), ("Ablaincourt_",
             "wind_speed_rel_err_max": float(err_ws.max()), "wind_direction_abs_err_max_deg": float(np.abs(wdl - ref["wd_local"]).max()),
             "ti_flip_fraction": float(np.mean(ti_jump)), "order_exact": bool(np.array_equal(fb.get_state("order"), ref["order"])),
             "oracle_seconds": t_ref,
+            "envs_resolved_in_fp64": int(fb.get_state("ambiguous").sum()) if (precision == "f32" and strict) else 0,
         }
-        out[f"{name}{precision}"] = rec
-        print(name, precision, rec, flush=True)
+        tag = precision + ("" if strict or precision == "f64" else "_relaxed")
+        out[f"{name}{tag}"] = rec
+        print(name, tag, rec, flush=True)
         fb.close()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/parity_sweep.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/r2_parity_sweep.json", "w"), indent=1)

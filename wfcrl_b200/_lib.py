@@ -32,7 +32,7 @@ class WfConfig(C.Structure):
         ("ch_initial", C.c_double), ("ch_constant", C.c_double), ("ch_ai", C.c_double), ("ch_downstream", C.c_double),
         ("rotor_diameter", C.c_double), ("hub_height", C.c_double), ("tsr", C.c_double), ("pP", C.c_double),
         ("pT", C.c_double), ("generator_efficiency", C.c_double), ("ref_density_cp_ct", C.c_double),
-        ("table_len", C.c_int32), ("reserved1", C.c_int32),
+        ("table_len", C.c_int32), ("turbine_grid_points", C.c_int32),
         ("table_ws", C.c_double * WF_TABLE_MAX), ("table_cp", C.c_double * WF_TABLE_MAX),
         ("table_ct", C.c_double * WF_TABLE_MAX),
     ]

@@ -148,6 +148,10 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if (cfg->wind_veer != 0.0) return set_err(WF_ERR_INVALID, "wind_veer != 0 is not supported (case.yaml:39 uses 0)");
     if (!(cfg->yaw_lo < cfg->yaw_hi)) return set_err(WF_ERR_INVALID, "yaw bounds: need low < high (mdp.py:196)");
     if (cfg->precision != WF_PREC_F64 && cfg->precision != WF_PREC_F32) return set_err(WF_ERR_INVALID, "bad precision");
+    if (cfg->turbine_grid_points != 0 && cfg->turbine_grid_points != 3 && cfg->turbine_grid_points != 5)
+        return set_err(WF_ERR_INVALID, "turbine_grid_points must be 3 (case.yaml:16) or 5");
+    if (cfg->turbine_grid_points == 5 && cfg->kernel != WF_KERNEL_BASIC)
+        return set_err(WF_ERR_INVALID, "turbine_grid_points = 5 needs WF_KERNEL_BASIC (the tuned kernels are built for the 3x3 grid)");
     if (cfg->kernel != WF_KERNEL_BASIC && cfg->kernel != WF_KERNEL_FAST) return set_err(WF_ERR_INVALID, "bad kernel");
     if (!(cfg->rotor_diameter > 0.0) || !(cfg->hub_height > cfg->rotor_diameter / 2) || !(cfg->dt > 0.0) ||
         !(cfg->actuator_rate > 0.0) || !(cfg->turbulence_intensity > 0.0) || !(cfg->air_density > 0.0))
@@ -181,6 +185,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     m.T = T; m.B = B;
     m.max_iter = cfg->max_iter; m.continuous = cfg->continuous_control; m.multi_agent = cfg->multi_agent;
     m.shaper = cfg->reward_shaper; m.table_len = cfg->table_len;
+    m.G = cfg->turbine_grid_points ? cfg->turbine_grid_points : 3;
     m.yaw_lo_f = (float)cfg->yaw_lo; m.yaw_hi_f = (float)cfg->yaw_hi; m.yaw_step_f = (float)cfg->yaw_step;
     m.rate_f = (float)cfg->actuator_rate; m.dt_f = (float)cfg->dt;
     m.amb_eps = getenv("WFCRL_B200_AMB_EPS") ? (float)atof(getenv("WFCRL_B200_AMB_EPS")) : kDefaultAmbEps;

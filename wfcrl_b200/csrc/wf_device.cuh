@@ -12,6 +12,7 @@
 struct WfModel {
     int T, B;
     int max_iter, continuous, multi_agent, shaper, table_len;
+    int G;                         // rotor grid points per side (case.yaml:16 turbine_grid_points): 3, or 5 with the basic kernels
     float yaw_lo_f, yaw_hi_f, yaw_step_f;  // float32 bounds exactly as gymnasium Box stores them (mdp.py:111-116,143-144)
     float rate_f, dt_f;
     int autoreset;                 // step kernels reset an env themselves when its step truncates (wf_set_autoreset)

@@ -19,6 +19,10 @@
 
 #include <math.h>
 
+#ifndef WF_VTAB64_PF_DIST
+#define WF_VTAB64_PF_DIST 1  // table rows of source i + 1 are prefetched to L2 while source i is processed (2: -4 %, 4: -8 %)
+#endif
+
 namespace {
 
 constexpr double kPi = 3.141592653589793;
@@ -90,9 +94,9 @@ __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double
 struct SmemView64 {
     double2* vw;              // [9T] (v, w) per rotor point
     double* wsq;              // [9T] running sum of squared deficits
-    double *xs, *ys, *xi, *yi;  // [T] sorted rotated coordinates and numpy-order grid means
+    double *xs, *ys;          // [T] sorted rotated coordinates (the sources' grid means x_i, y_i are read from global memory)
     double* tia;              // [3T]
-    double *cyaw, *syaw, *yawd;  // [T] cos / sin / degrees of the yaw (sorted order)
+    double *cyaw, *syaw;      // [T] cos / sin of the yaw (sorted order)
     double* tifin;            // [T]
     double* ynew;             // [T] new yaw, degrees, ORIGINAL order
     uchar4* idx;              // [T]
@@ -104,9 +108,9 @@ __host__ __device__ inline size_t fast64_smem_bytes(int T) {
     size_t n = 0;
     n += (size_t)9 * T * 16;  // vw
     n += (size_t)9 * T * 8;   // wsq
-    n += (size_t)4 * T * 8;   // xs, ys, xi, yi
+    n += (size_t)2 * T * 8;   // xs, ys
     n += (size_t)3 * T * 8;   // tia
-    n += (size_t)5 * T * 8;   // cyaw, syaw, yawd, tifin, ynew
+    n += (size_t)4 * T * 8;   // cyaw, syaw, tifin, ynew
     n += (size_t)T * 4;       // idx
     n += (size_t)2 * ((T + 15) / 16 * 16);
     return (n + 15) / 16 * 16;
@@ -119,12 +123,9 @@ __device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T) {
     s.wsq = f; f += 9 * T;
     s.xs = f; f += T;
     s.ys = f; f += T;
-    s.xi = f; f += T;
-    s.yi = f; f += T;
     s.tia = f; f += 3 * T;
     s.cyaw = f; f += T;
     s.syaw = f; f += T;
-    s.yawd = f; f += T;
     s.tifin = f; f += T;
     s.ynew = f; f += T;
     s.idx = (uchar4*)f;
@@ -186,8 +187,6 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         sm.ynew[tt] = ynew;
         sm.xs[tt] = s.xs[row + tt];
         sm.ys[tt] = s.ys[row + tt];
-        sm.xi[tt] = s.xi[row + tt];
-        sm.yi[tt] = s.yi[row + tt];
         sm.idx[tt] = s.idx[row + tt];
         sm.ordr[tt] = (unsigned char)s.order[row + tt];
     }
@@ -198,7 +197,6 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double yd = sm.ynew[sm.ordr[tt]];
         double sy, cy;
         sincos(yd * kRad, &sy, &cy);
-        sm.yawd[tt] = yd;
         sm.cyaw[tt] = cy;
         sm.syaw[tt] = sy;
     }
@@ -225,10 +223,13 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     // vortex table of this env (wf_device.cuh), or NULL: evaluate every pair directly
     const double* __restrict__ vrow = nullptr;
     if (use_vtab && s.vtab64 && s.vtab_ok[b]) vrow = s.vtab64 + (size_t)b * ((size_t)T * (T - 1) / 2) * 36;
-    if (vrow && warp == 0) { prefetch_rows64(vrow, 0, T, lane, 288); prefetch_rows64(vrow, 1, T, lane, 288); }
+    if (vrow && warp == 0) {
+#pragma unroll
+        for (int d = 0; d < WF_VTAB64_PF_DIST; ++d) prefetch_rows64(vrow, d, T, lane, 288);
+    }
 
     for (int i = 0; i < T; ++i) {
-        if (vrow && warp == 0) prefetch_rows64(vrow, i + 2, T, lane, 288);
+        if (vrow && warp == 0) prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
         // ===== source prologue (every warp on its own: all values below are block-uniform) =====
         double su3, sv, sw, vq, wwq;
         {
@@ -253,7 +254,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double avg = cbrt64(su3 * (1.0 / 9.0));
 #endif
         const double ct_raw = dclamp(interp_d(fc, fc.tab_ct, avg, 0.0001, 0.9999), 0.0001, 0.9999);
-        const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.yawd[i];
+        const double cy = sm.cyaw[i], sy = sm.syaw[i], yd = sm.ynew[sm.ordr[i]];
         const double ct = ct_raw * cy;
         // The chain below is the critical path of the FP64 kernels (one warp, dependent double-precision operations): divisions
         // are shared through reciprocals and identities that hold to rounding (1e-16, the tolerance is 1e-9) are used freely.
@@ -367,7 +368,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
 #endif
 
         const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
-        const double x_i = sm.xi[i], y_i = sm.yi[i];
+        const double x_i = __ldg(s.xi + row + i), y_i = __ldg(s.yi + row + i);  // block-uniform, L1-resident
 
         constexpr double kCut = 9.5;
         const double reach1 = kCut * kyv;
@@ -652,7 +653,9 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     }
 }
 
-__global__ void __launch_bounds__(32, 4)
+// 12 CTAs per SM: the register file is split over the 4 SM sub-partitions (16 K registers each), so a one-warp CTA needs
+// <= 168 registers for three of them to share a sub-partition (192 would leave two: 8 per SM)
+__global__ void __launch_bounds__(32, 12)
 wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
                       const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                       const double* __restrict__ yaw_cmd, const WfOutPtrs out) {

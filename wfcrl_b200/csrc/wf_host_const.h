@@ -21,6 +21,7 @@ static inline void wf_fill_default_config(WfConfig* c) {
     c->air_density = 1.225; c->turbulence_intensity = 0.06; c->wind_shear = 0.12; c->wind_veer = 0.0;
     c->alpha = 0.58; c->beta = 0.077; c->ka = 0.38; c->kb = 0.004; c->ad = 0.0; c->bd = 0.0; c->dm = 1.0;
     c->ch_initial = 0.1; c->ch_constant = 0.5; c->ch_ai = 0.8; c->ch_downstream = -0.32;
+    c->turbine_grid_points = 3;                               // case.yaml:16
     c->rotor_diameter = 126.0; c->hub_height = 90.0; c->tsr = 8.0; c->pP = 1.88; c->pT = 1.88;
     c->generator_efficiency = 1.0; c->ref_density_cp_ct = 1.225;
     // nrel_5MW power/thrust table as shipped with FLORIS 3.x

@@ -56,11 +56,39 @@ template <> struct M<float> {
     static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
 };
 
-// numpy's reduction order over the 9 contiguous grid values (pairwise over the first 8, then the 9th)
-template <typename R> __device__ __forceinline__ R sum9(const R* p) {
-    return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
+// numpy's reduction order over N < 128 contiguous values (pairwise_sum: eight running sums over the blocks of 8, combined
+// pairwise, then the remainder one by one); N = 9 and 25 are the 3x3 and 5x5 rotor grids
+template <typename R, int N> __device__ __forceinline__ R sumN(const R* p) {
+    static_assert(N >= 8 && N < 128, "grid of 3x3 .. 11x11 points");
+    R r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = p[q];
+#pragma unroll
+    for (int i = 8; i < N - (N % 8); i += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] += p[i + q];
+    }
+    R res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = N - (N % 8); i < N; ++i) res += p[i];
+    return res;
 }
-template <typename R> __device__ __forceinline__ R mean9(const R* p) { return M<R>::div(sum9(p), R(9)); }
+template <typename R, int N> __device__ __forceinline__ R meanN(const R* p) { return M<R>::div(sumN<R, N>(p), R(N)); }
+// the same at run time (geometry kernel)
+__device__ __forceinline__ double np_mean(const double* p, int n) {
+    double r[8];
+    for (int q = 0; q < 8; ++q) r[q] = p[q];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], p[i + q]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, p[i]);
+    return __ddiv_rn(res, (double)n);
+}
+// offset of grid index q on a G-point rotor grid: np.linspace(-D/4, D/4, G)[q]
+__device__ __forceinline__ double grid_off(double quarter_D, int q, int G) {
+    return q == G - 1 ? quarter_D : __dadd_rn(__dmul_rn((double)q, __ddiv_rn(2.0 * quarter_D, (double)(G - 1))), -quarter_D);
+}
 
 // np.interp + scipy interp1d fill values on the turbine table (table lives in global memory, L1-resident)
 __device__ __forceinline__ double interp_table(double x, const double* __restrict__ xp, const double* __restrict__ fp,
@@ -83,15 +111,15 @@ __device__ __forceinline__ double interp_table(double x, const double* __restric
 // shared-memory layouts
 // ---------------------------------------------------------------------------------------------------------------
 // Per-env constants computed once per step by thread 0.
-template <typename R> struct EnvConst {
-    R U0[3], nu4[3];       // initial velocity per vertical index k; 4*nu/Uinf per k (transverse-velocity decay)
-    R zq[6][3];            // Z_k + c_v + NUM_EPS for the 6 vortices (top, bottom, top-mirror, bottom-mirror, core, core-mirror)
+template <typename R, int G> struct EnvConst {
+    R U0[G], nu4[G];       // initial velocity per vertical index k; 4*nu/Uinf per k (transverse-velocity decay)
+    R zq[6][G];            // Z_k + c_v + NUM_EPS for the 6 vortices (top, bottom, top-mirror, bottom-mirror, core, core-mirror)
     R Uinf, vel_top, vel_bot, eps2, inv_eps2, I0;
     double wd, ws;
 };
 
 // Per-source broadcast record (double buffered).
-template <typename R> struct SrcRec {
+template <typename R, int NP> struct SrcRec {
     double x_i, y_i;       // FP64: every x-mask is decided on the FP64 difference X - x_i
     R ct, a, Gt, Gb, Gwr;  // thrust coeff (incl. cos yaw), axial induction, vortex circulations
     R cgv;                 // cosd(-yaw_i)
@@ -101,15 +129,15 @@ template <typename R> struct SrcRec {
     R near_s;              // 0.501 * D * sqrt(ct / 2)
     R ctc;                 // ct * cosd(-yaw_i) * D^2 / 8
     R watK;                // constant * a^ai * I0^initial
-    R x0d[WF_NP], kyd[WF_NP];  // near-wake length (relative to x_i) and expansion rate from the PRE-update TI
-    R x0v[WF_NP], kyv[WF_NP];  // same from the POST-update TI (velocity model)
+    R x0d[NP], kyd[NP];  // near-wake length (relative to x_i) and expansion rate from the PRE-update TI
+    R x0v[NP], kyv[NP];  // same from the POST-update TI (velocity model)
 };
 
 // The six vortices of calculate_transverse_velocity in FLORIS' summation order V1..V6:
 //   V1 top (+Gt), V2 bottom (+Gb), V3 top ground mirror (-Gt), V4 bottom ground mirror (-Gb),
 //   V5 wake rotation (+Gwr), V6 wake rotation ground mirror (-Gwr).
-template <typename R>
-__device__ __forceinline__ void transverse(const EnvConst<R>& ec, R Gt, R Gb, R Gwr, R yL, int k, R decay, R* V, R* W) {
+template <typename R, int G>
+__device__ __forceinline__ void transverse(const EnvConst<R, G>& ec, R Gt, R Gb, R Gwr, R yL, int k, R decay, R* V, R* W) {
     const R two_pi = R(2.0 * kPi);
     const R yy = yL * yL;
     R Vs = R(0), Ws = R(0);
@@ -192,13 +220,22 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
         s.xs[o] = x;
         s.ys[o] = y;
         s.order[o] = t;
-        s.xi[o] = __ddiv_rn(__dadd_rn(__dmul_rn(8.0, x), x), 9.0);
-        const double off = 0.5 * m.D / 2;  // disc_area_radius: grid offsets -off, 0, +off
-        const double ya = __dadd_rn(y, -off), yb = __dadd_rn(y, 0.0), yc = __dadd_rn(y, off);
-        // flattened grid values p = 3j + k: ya ya ya yb yb yb yc yc yc ; numpy order ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) + p8
-        const double s03 = __dadd_rn(__dadd_rn(ya, ya), __dadd_rn(ya, yb));
-        const double s47 = __dadd_rn(__dadd_rn(yb, yb), __dadd_rn(yc, yc));
-        s.yi[o] = __ddiv_rn(__dadd_rn(__dadd_rn(s03, s47), yc), 9.0);
+        const double off = 0.5 * m.D / 2;  // disc_area_radius: grid offsets np.linspace(-off, off, G)
+        if (m.G == 3) {
+            s.xi[o] = __ddiv_rn(__dadd_rn(__dmul_rn(8.0, x), x), 9.0);
+            const double ya = __dadd_rn(y, -off), yb = __dadd_rn(y, 0.0), yc = __dadd_rn(y, off);
+            // flattened grid values p = 3j + k: ya ya ya yb yb yb yc yc yc ; numpy order ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) + p8
+            const double s03 = __dadd_rn(__dadd_rn(ya, ya), __dadd_rn(ya, yb));
+            const double s47 = __dadd_rn(__dadd_rn(yb, yb), __dadd_rn(yc, yc));
+            s.yi[o] = __ddiv_rn(__dadd_rn(__dadd_rn(s03, s47), yc), 9.0);
+        } else {  // any other grid: the same numpy reduction over the G*G flattened values p = G*j + k
+            double gx[49], gy[49];
+            const int G = m.G;
+            for (int j = 0; j < G; ++j)
+                for (int q = 0; q < G; ++q) { gx[G * j + q] = x; gy[G * j + q] = __dadd_rn(y, grid_off(off, j, G)); }
+            s.xi[o] = np_mean(gx, G * G);
+            s.yi[o] = np_mean(gy, G * G);
+        }
         // float-float positions relative to the rotation centre for the FP32 kernel
         const double xrel = x - m.xc, yrel = y - m.yc;
         const float xh = (float)xrel, yh = (float)yrel;
@@ -335,7 +372,7 @@ __global__ void wf_reset_state_kernel(const WfModel m, const WfState s, const ui
 // ---------------------------------------------------------------------------------------------------------------
 // step kernel (basic variant)
 // ---------------------------------------------------------------------------------------------------------------
-template <typename R>
+template <typename R, int G>
 __global__ void __launch_bounds__(WF_MAX_TURBINES_K)
 wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const WfState s,
                      const uint8_t* __restrict__ mask, const float* __restrict__ action,
@@ -346,14 +383,18 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
     const int t = threadIdx.x;
     const size_t row = (size_t)b * T;
 
-    __shared__ EnvConst<R> ec;
-    __shared__ SrcRec<R> rec[2];
+    constexpr int NP = G * G;  // rotor grid points (case.yaml:16 turbine_grid_points = G), p = G*j + k, j lateral, k vertical
+    __shared__ EnvConst<R, G> ec;
+    __shared__ SrcRec<R, NP> rec[2];
     __shared__ double sh_yaw[WF_MAX_TURBINES_K];   // new yaw in ORIGINAL order
     __shared__ double sh_red0[WF_MAX_TURBINES_K];  // reward reduction scratch (original order)
     __shared__ double sh_red1[WF_MAX_TURBINES_K];
 
     const R D = (R)m.D, HH = (R)m.HH;
-    const double offd = 0.5 * m.D / 2;
+    const double qD = 0.5 * m.D / 2;  // grid offsets = np.linspace(-qD, qD, G)
+    double offs[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) offs[q] = grid_off(qD, q, G);
 
     // ---- env prologue: thread t handles ORIGINAL turbine t (mdp.py:291-319, simple_env.py:64-72) ----------------
     int nm = 0;
@@ -392,16 +433,16 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
         const double eps = 0.2 * m.D;
         ec.eps2 = (R)(eps * eps);
         ec.inv_eps2 = (R)(1.0 / (eps * eps));
-        double U0[3], usum = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            const double Z = m.HH + (k - 1) * offd;
+        double U0[G], usum = 0.0;
+        for (int k = 0; k < G; ++k) {
+            const double Z = m.HH + offs[k];
             U0[k] = ws * pow(Z / m.HH, m.shear);
             usum += U0[k];
         }
-        const double Uinf = usum / 3.0;
+        const double Uinf = usum / G;
         ec.Uinf = (R)Uinf;
-        for (int k = 0; k < 3; ++k) {
-            const double Z = m.HH + (k - 1) * offd;
+        for (int k = 0; k < G; ++k) {
+            const double Z = m.HH + offs[k];
             const double dU = ws * (m.shear * pow(1.0 / m.HH, m.shear) * pow(Z, m.shear - 1.0));
             const double lmda = m.D / 8, kappa = 0.41;
             const double lm = kappa * Z / (1 + kappa * Z / lmda);
@@ -417,7 +458,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
     __syncthreads();
 
     // ---- per-thread state: turbine at sorted position t ----------------------------------------------------------
-    R wake[WF_NP], v[WF_NP], w[WF_NP], ti[WF_NP];
+    R wake[NP], v[NP], w[NP], ti[NP];
     double X = 0.0, Ys = 0.0, yaw_t = 0.0;
     int orig = 0;
     if (t < T) {
@@ -427,20 +468,20 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
         yaw_t = sh_yaw[orig];
     }
 #pragma unroll
-    for (int p = 0; p < WF_NP; ++p) { wake[p] = R(0); v[p] = R(0); w[p] = R(0); ti[p] = ec.I0; }
+    for (int p = 0; p < NP; ++p) { wake[p] = R(0); v[p] = R(0); w[p] = R(0); ti[p] = ec.I0; }
     const R I0 = ec.I0;
     const R inv_D = M<R>::div(R(1), D);
 
     // ---- sequential solver over sources ---------------------------------------------------------------------------
     for (int i = 0; i < T; ++i) {
-        SrcRec<R>& rc = rec[i & 1];
+        SrcRec<R, NP>& rc = rec[i & 1];
         if (t == i) {
             // ===== source prologue (A.4, A.5, source part of A.6-A.8) =====
             const double x_i = s.xi[row + i], y_i = s.yi[row + i];
-            R u[WF_NP], c3[WF_NP];
+            R u[NP], c3[NP];
 #pragma unroll
-            for (int p = 0; p < WF_NP; ++p) { u[p] = ec.U0[p % 3] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
-            const R avg = M<R>::cbrt(mean9(c3));
+            for (int p = 0; p < NP; ++p) { u[p] = ec.U0[p % G] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
+            const R avg = M<R>::cbrt(meanN<R, NP>(c3));
             double ctd = interp_table((double)avg, m.tab_ws, m.tab_ct, m.table_len, 0.0001, 0.9999);
             ctd = fmin(fmax(ctd, 0.0001), 0.9999);
             R sy, cy;
@@ -453,11 +494,11 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
             const R Gt = sy * cy * G_top0, Gb = -(sy * cy * G_bot0);
 
             // A.5 secondary steering on the source's own grid: top (+G_top0), bottom (-G_bot0), wake rotation
-            R vt[WF_NP], vb[WF_NP], vc[WF_NP];
+            R vt[NP], vb[NP], vc[NP];
 #pragma unroll
-            for (int p = 0; p < WF_NP; ++p) {
-                const int j = p / 3, k = p % 3;
-                const R yL = Lat<R>::get(Ys, y_i, (j - 1) * offd) + (R)kNumEps;
+            for (int p = 0; p < NP; ++p) {
+                const int j = p / G, k = p % G;
+                const R yL = Lat<R>::get(Ys, y_i, offs[j]) + (R)kNumEps;
                 const R yy = yL * yL;
                 const R two_pi = R(2.0 * kPi);
                 R zz = ec.zq[0][k], r = yy + zz * zz;
@@ -467,7 +508,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 zz = ec.zq[4][k]; r = yy + zz * zz;
                 vc[p] = M<R>::div(Gwr * zz, two_pi * r) * (R(1) - M<R>::exp(-r * ec.inv_eps2));
             }
-            R val = M<R>::div(R(2) * (mean9(v) - mean9(vc)), mean9(vt) + mean9(vb));
+            R val = M<R>::div(R(2) * (meanN<R, NP>(v) - meanN<R, NP>(vc)), meanN<R, NP>(vt) + meanN<R, NP>(vb));
             val = M<R>::min(M<R>::max(val, R(-1)), R(1));
             const R eff_yaw = (R)yaw_t + (R)(180.0 / kPi) * (R(0.5) * M<R>::asin(val));
 
@@ -493,7 +534,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 rc.sy0d = sy0;
                 rc.sz0d = sz0;
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) {
+                for (int p = 0; p < NP; ++p) {
                     rc.x0d[p] = M<R>::div(D * (cg * (R(1) + sq1ctcg)),
                                           (R)1.4142135623730951 * (R(4) * (R)m.alpha * ti[p] + R(2) * (R)m.beta * (R(1) - sq1ct)));
                     rc.kyd[p] = (R)m.ka * ti[p] + (R)m.kb;
@@ -503,18 +544,18 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
             // own transverse velocities (A.7) -> yaw-added recovery TI update (in place) -> own v, w updated now
             {
                 const double dxs = X - x_i;
-                R Vp[WF_NP], Wp[WF_NP];
+                R Vp[NP], Wp[NP];
                 if (dxs < 0.0) {
 #pragma unroll
-                    for (int p = 0; p < WF_NP; ++p) { Vp[p] = R(0); Wp[p] = R(0); }
+                    for (int p = 0; p < NP; ++p) { Vp[p] = R(0); Wp[p] = R(0); }
                 } else {
                     const R dx = (R)dxs;
 #pragma unroll
-                    for (int p = 0; p < WF_NP; ++p) {
-                        const int j = p / 3, k = p % 3;
-                        const R yL = Lat<R>::get(Ys, y_i, (j - 1) * offd) + (R)kNumEps;
+                    for (int p = 0; p < NP; ++p) {
+                        const int j = p / G, k = p % G;
+                        const R yL = Lat<R>::get(Ys, y_i, offs[j]) + (R)kNumEps;
                         const R decay = M<R>::div(ec.eps2, ec.nu4[k] * dx + ec.eps2);
-                        transverse<R>(ec, Gt, Gb, Gwr, yL, k, decay, &Vp[p], &Wp[p]);
+                        transverse<R, G>(ec, Gt, Gb, Gwr, yL, k, decay, &Vp[p], &Wp[p]);
                         Wp[p] = M<R>::max(Wp[p], R(0));
                     }
                 }
@@ -522,15 +563,15 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 const R aI = avg * I;
                 const R kk = M<R>::div(aI * aI, (R)(2.0 / 3.0));
                 const R u_term = M<R>::sqrt(R(2) * kk);
-                R tv[WF_NP], tw[WF_NP];
+                R tv[NP], tw[NP];
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) { tv[p] = v[p] + Vp[p]; tw[p] = w[p] + Wp[p]; }
-                const R v_term = mean9(tv), w_term = mean9(tw);
+                for (int p = 0; p < NP; ++p) { tv[p] = v[p] + Vp[p]; tw[p] = w[p] + Wp[p]; }
+                const R v_term = meanN<R, NP>(tv), w_term = meanN<R, NP>(tw);
                 const R k_total = R(0.5) * (u_term * u_term + v_term * v_term + w_term * w_term);
                 const R I_total = M<R>::div(M<R>::sqrt((R)(2.0 / 3.0) * k_total), avg);
                 const R I_mix = I_total - I;
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) { ti[p] = ti[p] + R(2) * I_mix; v[p] = tv[p]; w[p] = tw[p]; }
+                for (int p = 0; p < NP; ++p) { ti[p] = ti[p] + R(2) * I_mix; v[p] = tv[p]; w[p] = tw[p]; }
             }
 
             // A.8 velocity-model scalars with the UPDATED TI (uses yaw_i, opposite sign: cos(-yaw) = cy)
@@ -544,7 +585,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 rc.near_s = R(0.501) * D * M<R>::sqrt(ct * R(0.5));
                 rc.ctc = ct * cgv * D * D * R(0.125);
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) {
+                for (int p = 0; p < NP; ++p) {
                     rc.x0v[p] = M<R>::div(D * cgv * (R(1) + sq1ct),
                                           (R)1.4142135623730951 * (R(4) * (R)m.alpha * ti[p] + R(2) * (R)m.beta * (R(1) - sq1ct)));
                     rc.kyv[p] = (R)m.ka * ti[p] + (R)m.kb;
@@ -569,17 +610,17 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 const bool gt0 = X > rc.x_i;
                 const bool le15 = X <= __dadd_rn(15 * m.D, rc.x_i);
                 const R Gt = rc.Gt, Gb = rc.Gb, Gwr = rc.Gwr;
-                R dU[WF_NP];
+                R dU[NP];
                 int cnt = 0;
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) {
-                    const int j = p / 3, k = p % 3;
-                    const R dyc = Lat<R>::get(Ys, rc.y_i, (j - 1) * offd);  // Y - y_i
+                for (int p = 0; p < NP; ++p) {
+                    const int j = p / G, k = p % G;
+                    const R dyc = Lat<R>::get(Ys, rc.y_i, offs[j]);  // Y - y_i
                     // -- transverse velocities
                     {
                         const R decay = M<R>::div(ec.eps2, ec.nu4[k] * dx + ec.eps2);
                         R Vq, Wq;
-                        transverse<R>(ec, Gt, Gb, Gwr, dyc + (R)kNumEps, k, decay, &Vq, &Wq);
+                        transverse<R, G>(ec, Gt, Gb, Gwr, dyc + (R)kNumEps, k, decay, &Vq, &Wq);
                         v[p] += Vq;
                         w[p] += M<R>::max(Wq, R(0));
                     }
@@ -617,7 +658,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                                 sgz = down * rc.near_s + up * rc.sz0v;
                             }
                             const R dy = dyc - defl;
-                            const R dz = (R)((k - 1) * offd);
+                            const R dz = (R)(offs[k]);
                             const R r = M<R>::div(dy * dy, R(2) * sgy * sgy) + M<R>::div(dz * dz, R(2) * sgz * sgz);
                             R d = R(1) - M<R>::div(rc.ctc, sgy * sgz);
                             d = M<R>::min(M<R>::max(d, R(0)), R(1));
@@ -632,12 +673,12 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
                 if (cnt > 0 && gt0 && le15) {
                     const R dxp = dx + ((dxd <= 0.1) ? R(1) : R(0));
                     const R wat = rc.watK * M<R>::pow(dxp * inv_D, (R)m.ch_down);
-                    ti_add_base = ((R)cnt * (R)(1.0 / 9.0)) * wat;
+                    ti_add_base = ((R)cnt * (R)(1.0 / NP)) * wat;
                 }
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) {
-                    const int j = p / 3;
-                    const R dyc = Lat<R>::get(Ys, rc.y_i, (j - 1) * offd);
+                for (int p = 0; p < NP; ++p) {
+                    const int j = p / G;
+                    const R dyc = Lat<R>::get(Ys, rc.y_i, offs[j]);
                     const R ta = (M<R>::abs(dyc) < R(2) * D) ? ti_add_base : R(0);
                     ti[p] = M<R>::max(M<R>::sqrt(ta * ta + I0 * I0), ti[p]);
                     wake[p] = M<R>::hypot(wake[p], dU[p]);
@@ -650,29 +691,29 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
     const bool env = (mode != WF_MODE_INTERFACE);
     R p_out = R(0), lsum = R(0);
     if (t < T) {
-        R u[WF_NP], c3[WF_NP], dd[WF_NP];
+        R u[NP], c3[NP], dd[NP];
 #pragma unroll
-        for (int p = 0; p < WF_NP; ++p) { u[p] = ec.U0[p % 3] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
-        const R avg = M<R>::cbrt(mean9(c3));
+        for (int p = 0; p < NP; ++p) { u[p] = ec.U0[p % G] - wake[p]; c3[p] = u[p] * u[p] * u[p]; }
+        const R avg = M<R>::cbrt(meanN<R, NP>(c3));
         R sy, cy;
         M<R>::sincos((R)(yaw_t * (kPi / 180.0)), &sy, &cy);
         const double veff = (double)((R)cbrt(m.rho / m.ref_rho) * avg * M<R>::pow(cy, (R)(m.pP / 3.0)));
         const double pw = interp_table(veff, m.tab_ws, m.tab_pw, m.table_len, 0.0, 0.0) * m.ref_rho;  // [W]
 #pragma unroll
-        for (int p = 0; p < WF_NP; ++p) dd[p] = (R)ec.wd - (R)(180.0 / kPi) * M<R>::atan2(v[p], u[p]);
-        R wdl = mean9(dd);
+        for (int p = 0; p < NP; ++p) dd[p] = (R)ec.wd - (R)(180.0 / kPi) * M<R>::atan2(v[p], u[p]);
+        R wdl = meanN<R, NP>(dd);
         R wsl = avg;
-        const R ti_m = mean9(ti);
+        const R ti_m = meanN<R, NP>(ti);
         R sd[3];
         {
             const R* arrs[3] = {u, v, w};
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const R mu = mean9(arrs[q]);
-                R d2[WF_NP];
+                const R mu = meanN<R, NP>(arrs[q]);
+                R d2[NP];
 #pragma unroll
-                for (int p = 0; p < WF_NP; ++p) { const R e = arrs[q][p] - mu; d2[p] = e * e; }
-                sd[q] = M<R>::sqrt(mean9(d2));
+                for (int p = 0; p < NP; ++p) { const R e = arrs[q][p] - mu; d2[p] = e * e; }
+                sd[q] = M<R>::sqrt(meanN<R, NP>(d2));
             }
         }
         R loads[4] = {ti_m, sd[0], sd[1], sd[2]};
@@ -791,21 +832,21 @@ cudaError_t wf_launch_step_basic(int precision, int mode, const WfModel& m, cons
                                  const float* d_action, const double* d_yaw_cmd, const WfOutPtrs& out,
                                  int env_begin, int env_count, cudaStream_t stream) {
     const int threads = round_up_warp(m.T);
-    if (precision == 0)
-        wf_step_basic_kernel<double><<<env_count, threads, 0, stream>>>(mode, env_begin, m, s, d_mask, d_action, d_yaw_cmd, out);
-    else
-        wf_step_basic_kernel<float><<<env_count, threads, 0, stream>>>(mode, env_begin, m, s, d_mask, d_action, d_yaw_cmd, out);
+#define WF_GO(R_, G_) wf_step_basic_kernel<R_, G_><<<env_count, threads, 0, stream>>>(mode, env_begin, m, s, d_mask, d_action, d_yaw_cmd, out)
+    if (m.G == 5) { if (precision == 0) WF_GO(double, 5); else WF_GO(float, 5); }
+    else { if (precision == 0) WF_GO(double, 3); else WF_GO(float, 3); }
+#undef WF_GO
     return cudaGetLastError();
 }
 
 cudaError_t wf_step_basic_attributes(int precision, cudaFuncAttributes* attr, int* ctas_per_sm, int threads) {
     cudaError_t e;
     if (precision == 0) {
-        e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<double>);
+        e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<double, 3>);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<double>, threads, 0);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<double, 3>, threads, 0);
     }
-    e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<float>);
+    e = cudaFuncGetAttributes(attr, wf_step_basic_kernel<float, 3>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<float>, threads, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_basic_kernel<float, 3>, threads, 0);
 }

@@ -3,8 +3,8 @@ wfcrl/interface.py:462-479; the file is written from wfcrl/simulators/floris/inp
 ``create_floris_case``, wfcrl/simul_utils.py:34-48).
 
 The CUDA path implements the model that template selects -- Gauss velocity deficit + Gauss deflection + Crespo-Hernandez
-turbulence + SOSFS combination with secondary steering, yaw-added recovery and transverse velocities on a 3x3 rotor grid of
-``nrel_5MW`` turbines.  This module turns such a file into the layout, the initial wind and the numeric overrides of
+turbulence + SOSFS combination with secondary steering, yaw-added recovery and transverse velocities on a 3x3 rotor grid
+(5x5 through the basic kernels) of ``nrel_5MW`` turbines.  This module turns such a file into the layout, the initial wind and the numeric overrides of
 ``WfConfig``; anything the kernels do not implement (another wake model, a disabled GCH term, another grid or turbine) is
 refused loudly instead of being silently ignored.
 """
@@ -26,8 +26,9 @@ def parse_floris_config(config: Dict[str, Any]) -> Dict[str, Any]:
     """``config``: the parsed YAML.  Returns ``{"xcoords", "ycoords", "wind_speed", "wind_direction", "overrides"}`` where
     ``overrides`` maps ``WfConfig`` field names to values (see include/wfcrl_b200.h)."""
     solver = config.get("solver", {})
-    _need(solver.get("type", "turbine_grid") == "turbine_grid" and int(solver.get("turbine_grid_points", 3)) == 3,
-          "solver must be a turbine_grid with turbine_grid_points = 3")
+    grid_points = int(solver.get("turbine_grid_points", 3))
+    _need(solver.get("type", "turbine_grid") == "turbine_grid" and grid_points in (3, 5),
+          "solver must be a turbine_grid with turbine_grid_points = 3 (tuned kernels) or 5 (basic kernels)")
     farm = config["farm"]
     xs, ys = [float(v) for v in farm["layout_x"]], [float(v) for v in farm["layout_y"]]
     _need(len(xs) == len(ys) and len(xs) >= 1, "layout_x and layout_y must have the same non-zero length")
@@ -38,7 +39,7 @@ def parse_floris_config(config: Dict[str, Any]) -> Dict[str, Any]:
     speeds, directions = flow.get("wind_speeds", [8.0]), flow.get("wind_directions", [270.0])
     _need(len(speeds) == 1 and len(directions) == 1, "exactly one wind speed and one wind direction")
     _need(float(flow.get("reference_wind_height", -1)) in (-1.0, 90.0), "reference_wind_height must be the hub height (-1)")
-    overrides = {"air_density": float(flow.get("air_density", 1.225)),
+    overrides = {"turbine_grid_points": grid_points, "air_density": float(flow.get("air_density", 1.225)),
                  "turbulence_intensity": float(flow.get("turbulence_intensity", 0.06)),
                  "wind_shear": float(flow.get("wind_shear", 0.12)), "wind_veer": float(flow.get("wind_veer", 0.0))}
 

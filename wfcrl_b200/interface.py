@@ -98,6 +98,8 @@ class FlorisInterface(BaseInterface):
         assert len(xcoords) == num_turbines == len(ycoords)
         self.num_turbines = num_turbines
         self._torch = torch
+        if overrides and overrides.get("turbine_grid_points", 3) != 3:
+            kernel = "basic"  # the tuned kernels are built for the template's 3x3 rotor grid
         self.fi = FlorisBatch(xcoords, ycoords, 1, device=device, precision=precision, kernel=kernel,
                               max_iter=int(max_iter), config_overrides=overrides)
         self.measure_map = self.DEFAULT_MEASURE_MAP
