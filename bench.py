@@ -45,6 +45,27 @@ def algorithmic_bytes(T: int) -> int:
     return 48 * T + 16
 
 
+def _e2e_roofline(world: int, e2e_value: float, envs_per_gpu: int, bytes_per_step: int):
+    """End-to-end bytes/s against the box's measured host<->device ceiling: the committed output of
+    tools/pcie_probe_multi.py (plain cudaMemcpyAsync with the same byte counts, one GPU alone and all 8 GPUs at once)."""
+    def probe(n):
+        path = os.path.join(ROOT, "profiles", f"r2_pcie_probe_{n}gpu.json")
+        if not os.path.exists(path):
+            return None
+        rec = json.load(open(path))
+        return max(rec["one_copy_per_direction"]["aggregate_GBps"], rec["library_pattern_6x9_copies"]["aggregate_GBps"])
+
+    alone, box = probe(1), probe(8)  # one GPU copying alone; all eight of the box at once (the host side's limit)
+    if alone is None and box is None:
+        return None
+    peak = min(v for v in ((alone * world) if alone else None, box) if v is not None)
+    n = "1 and 8" if alone and box else ("1" if alone else "8")
+    achieved = e2e_value / envs_per_gpu * bytes_per_step / 1e9
+    return {"bound": "host<->device copies (PCIe + host memory)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": f"min(n_gpus x one GPU copying alone, all 8 GPUs of the box copying at once) from "
+                           f"profiles/r2_pcie_probe_*gpu.json (probes available: {n} GPU(s))"}
+
+
 def _ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu --set full capture
     of this same command (profiles/ncu_traffic.json, written by hand from `ncu -i ... --page raw`); None if absent."""
@@ -588,7 +609,8 @@ def run_ours(args):
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "path": "FlorisBatch.step_host -> wf_step_host (pinned HOST action in, full step result out): "
-                            "6 env chunks, one stream each, H2D + kernel + D2H per chunk",
+                            "6 env chunks, one stream each, H2D + FP32 kernel + D2H per chunk, then ONE FP64 re-solve launch "
+                            "whose envs come back as compact records scattered into the caller's arrays",
                     "host_numa_binding": numa,
                     "observation_only_value": world * B * e2e_steps / e2e_obs_s,
                     "observation_only_d2h_bytes_per_step": int(d2h_obs),
@@ -596,6 +618,7 @@ def run_ours(args):
                     "zero_copy_path": "same call with WFCRL_B200_HOST_PATH=zero_copy: host buffers mapped into the step "
                                       "kernel, one launch, no copy engine (the library's default up to 163840 env x "
                                       "turbine elements, where it is faster)"},
+            "e2e_roofline": _e2e_roofline(world, world * B * e2e_steps / e2e_s, B, int(h2d) + int(d2h)),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -312,3 +312,35 @@ def test_step_is_cuda_graph_capturable(cuda_device):
     assert np.array_equal(graphed.get_state("num_iter"), eager.get_state("num_iter"))
     eager.close()
     graphed.close()
+
+
+def test_host_path_is_ordered_after_async_calls(cuda_device, monkeypatch):
+    """wf_step_host runs on the handle's own streams: it must wait for whatever the caller queued asynchronously on ITS stream
+    (device-side reset, wind update, device-side step) without an explicit synchronisation in between."""
+    import torch
+
+    from wfcrl_b200.backend import FlorisBatch
+
+    lx, ly = layout("Turb32_Row5_")
+    B, T = 4096, len(lx)
+    gen = torch.Generator().manual_seed(3)
+    acts = [(torch.rand(B, T, generator=gen) * 10 - 5).pin_memory() for _ in range(3)]
+    results = {}
+    for mode in ("racy", "synced"):
+        for path in ("staged", "zero_copy"):
+            monkeypatch.setenv("WFCRL_B200_HOST_PATH", path)
+            fb = FlorisBatch(lx, ly, B, precision="f32", kernel="fast", max_iter=100)
+            outs = []
+            for k, a in enumerate(acts):
+                fb.reset_sampled(None, seed=5 + k, env_id_offset=0)           # asynchronous: sampler, state, geometry, warm-up
+                fb.step(a.cuda(non_blocking=True))                             # asynchronous device-side step
+                if mode == "synced":
+                    torch.cuda.synchronize()
+                outs.append({key: v.clone() for key, v in fb.step_host(a).items()})
+            results[(mode, path)] = outs
+            fb.close()
+    monkeypatch.delenv("WFCRL_B200_HOST_PATH")
+    for path in ("staged", "zero_copy"):
+        for a, b in zip(results[("racy", path)], results[("synced", path)]):
+            for key in a:
+                assert torch.equal(a[key], b[key]), (path, key)
