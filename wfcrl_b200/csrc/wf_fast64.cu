@@ -73,6 +73,9 @@ __device__ __forceinline__ double cbrt64(double x) {  // x > 0
     return y;
 }
 
+// (Hand-rolled exp / log / asin / cos on the solver's argument ranges were tried and measured: the lean exp / log were 12-15 %
+// SLOWER than libdevice's on this kernel -- FP64 rounding and integer<->double conversions are slow-pipe operations -- and the
+// short asin / cos made no measurable difference; profiles/r2_vortex_table.md.)
 __device__ __forceinline__ double dclamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double* __restrict__ fp, double x, double left,
