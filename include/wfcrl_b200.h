@@ -217,6 +217,8 @@ int wf_set_turbulence_intensity(WfHandle h, const double* d_ti, void* stream);
  *   "nonfinite" i32[B] (guard counter: env steps whose reward was NaN/Inf since creation) |
  *   "episode" i32[B] (sampled resets so far: the counter word of wf_reset_sampled) |
  *   "ambiguous" u8[B] (strict FP32 handles: 1 = the last solve of this env was redone in FP64) |
+ *   episode bookkeeping kept by the env-mode step kernels: "ep_return" f64[B], "ep_len" i32[B] (running episode) and, over the
+ *   episodes the env has finished, "fin_sum" f64[B], "fin_sumsq" f64[B], "fin_n" i32[B], "fin_len" i64[B] |
  *   "ws" f64[B] | "wd" f64[B] | "ws_norm" f64[B] | "shaper_ref" f64[B] | "ti_ambient" f64[B] |
  *   "order" i32[B][T] | "xs" f64[B][T] | "ys" f64[B][T] | "xi" f64[B][T] | "yi" f64[B][T] | "cs" f64[B][2]
  * `bytes` must equal the full array size.

@@ -123,12 +123,15 @@ def test_make_vec_matches_oracle_with_autoreset(cuda_device, precision):
         assert np.allclose(fw[b], robs[b]["freewind_measurements"], rtol=1e-7 if precision == "f32" else 0, atol=0)
     rng = np.random.default_rng(0)
     n_trunc = 0
+    first_episode_return = np.zeros(B)
     for k in range(steps):
         a = rng.uniform(-5, 5, (B, 6)).astype(np.float32)
         obs, reward, term, trunc, info = env.step(torch.as_tensor(a, device="cuda"))
         rew = reward.double().cpu().numpy()
         tr = trunc.cpu().numpy()
         assert not term.any()
+        if n_trunc == 0:
+            first_episode_return += rew
         if k < max_steps - 1:
             for b, r in enumerate(refs):
                 o, rr, _t, rtr, _i = r.step({"yaw": a[b].copy()})
@@ -142,8 +145,10 @@ def test_make_vec_matches_oracle_with_autoreset(cuda_device, precision):
             # auto-reset: yaw back to zero, a fresh episode has started
             assert float(obs["yaw"].abs().max()) == 0.0
     assert n_trunc == 1
-    stats = env.episode_statistics()
+    stats = env.episode_statistics()   # from the sums the step kernels keep per env (no per-step host bookkeeping)
     assert stats["episodes"] == B and stats["length_mean"] == max_steps - 1
+    assert abs(stats["return_mean"] - first_episode_return.mean()) <= 1e-12 * abs(first_episode_return.mean())
+    assert np.allclose(env.episode_lengths.cpu().numpy(), steps - (max_steps - 1))   # the running (second) episode
     env.close()
 
 

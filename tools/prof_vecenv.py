@@ -3,9 +3,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from wfcrl_b200 import environments as envs
 
-env = envs.make_vec("HornsRev1_Floris", 8192, precision="f32", max_num_steps=100000)
+name, B = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("HornsRev1_Floris", 8192)
+env = envs.make_vec(name, B, precision="f32", max_num_steps=100000)
 obs = env.reset(seed=0)
-a = torch.randn(8192, 80, device="cuda")
+a = torch.randn(B, env.num_turbines, device="cuda")
+print(name, B)
 def timeit(fn, n=200):
     for _ in range(10): fn()
     torch.cuda.synchronize(); t0 = time.perf_counter()

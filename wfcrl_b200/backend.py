@@ -20,7 +20,9 @@ _SHAPER = {"none": _lib.SHAPER_NONE, "reference": _lib.SHAPER_REFERENCE_PCT, "st
 
 _STATE_DTYPES = {
     "yaw": (np.float64, "BT"), "acc": (np.float32, "BT"), "acc_prev": (np.float32, "BT"),
-    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "nonfinite": (np.int32, "B"), "episode": (np.int32, "B"), "ambiguous": (np.uint8, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
+    "num_iter": (np.int32, "B"), "num_moves": (np.int32, "B"), "nonfinite": (np.int32, "B"), "episode": (np.int32, "B"), "ambiguous": (np.uint8, "B"),
+    "ep_return": (np.float64, "B"), "ep_len": (np.int32, "B"), "fin_sum": (np.float64, "B"), "fin_sumsq": (np.float64, "B"),
+    "fin_n": (np.int32, "B"), "fin_len": (np.int64, "B"), "ws": (np.float64, "B"), "wd": (np.float64, "B"),
     "ws_norm": (np.float64, "B"), "shaper_ref": (np.float64, "B"), "ti_ambient": (np.float64, "B"),
     "order": (np.int32, "BT"), "xs": (np.float64, "BT"), "ys": (np.float64, "BT"), "xi": (np.float64, "BT"),
     "yi": (np.float64, "BT"), "cs": (np.float64, "B2"),
@@ -255,7 +257,7 @@ class FlorisBatch:
 
     # checkpoint / resume: the complete env state is a handful of small arrays
     _CHECKPOINT = ("yaw", "acc", "acc_prev", "num_iter", "num_moves", "nonfinite", "episode", "ws", "wd", "ws_norm", "shaper_ref",
-                   "ti_ambient")
+                   "ti_ambient", "ep_return", "ep_len", "fin_sum", "fin_sumsq", "fin_n", "fin_len")
 
     def state_dict(self) -> Dict[str, np.ndarray]:
         """Host copy of everything needed to resume the batch exactly where it is (geometry is rebuilt from wd)."""

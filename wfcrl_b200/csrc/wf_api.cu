@@ -233,7 +233,10 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
     if ((rc = dev_alloc(h, &s.yaw, BT)) || (rc = dev_alloc(h, &s.acc, BT)) || (rc = dev_alloc(h, &s.acc_prev, BT)) ||
         (rc = dev_alloc(h, &s.num_iter, (size_t)B)) || (rc = dev_alloc(h, &s.num_moves, (size_t)B)) ||
         (rc = dev_alloc(h, &s.nonfinite, (size_t)B)) || (rc = dev_alloc(h, &s.episode, (size_t)B)) || (rc = dev_alloc(h, &s.amb, (size_t)B)) ||
-        (rc = dev_alloc(h, &s.reset_mask, (size_t)B)) || (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)4 * WF_FIX_SLOTS)) ||
+        (rc = dev_alloc(h, &s.reset_mask, (size_t)B)) || (rc = dev_alloc(h, &s.ep_return, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.ep_len, (size_t)B)) || (rc = dev_alloc(h, &s.fin_sum, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.fin_sumsq, (size_t)B)) || (rc = dev_alloc(h, &s.fin_n, (size_t)B)) ||
+        (rc = dev_alloc(h, &s.fin_len, (size_t)B)) || (rc = dev_alloc(h, &s.fix_list, (size_t)B)) || (rc = dev_alloc(h, &s.fix_count, (size_t)4 * WF_FIX_SLOTS)) ||
         (rc = dev_alloc(h, &s.ws, (size_t)B)) || (rc = dev_alloc(h, &s.wd, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ws_norm, (size_t)B)) || (rc = dev_alloc(h, &s.shaper_ref, (size_t)B)) ||
         (rc = dev_alloc(h, &s.ti_amb, (size_t)B)) || (rc = dev_alloc(h, &s.xs, BT)) || (rc = dev_alloc(h, &s.ys, BT)) ||
@@ -644,7 +647,9 @@ static int find_state(WfHandle h, const char* name, void** p, size_t* bytes) {
     const WfState& s = h->st;
     struct { const char* n; void* p; size_t b; } tab[] = {
         {"yaw", s.yaw, BT * 8}, {"acc", s.acc, BT * 4}, {"acc_prev", s.acc_prev, BT * 4},
-        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"episode", s.episode, B * 4}, {"ambiguous", s.amb, B}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
+        {"num_iter", s.num_iter, B * 4}, {"num_moves", s.num_moves, B * 4}, {"nonfinite", s.nonfinite, B * 4}, {"episode", s.episode, B * 4}, {"ambiguous", s.amb, B},
+        {"ep_return", s.ep_return, B * 8}, {"ep_len", s.ep_len, B * 4}, {"fin_sum", s.fin_sum, B * 8},
+        {"fin_sumsq", s.fin_sumsq, B * 8}, {"fin_n", s.fin_n, B * 4}, {"fin_len", s.fin_len, B * 8}, {"ws", s.ws, B * 8}, {"wd", s.wd, B * 8},
         {"ws_norm", s.ws_norm, B * 8}, {"shaper_ref", s.shaper_ref, B * 8}, {"ti_ambient", s.ti_amb, B * 8},
         {"order", s.order, BT * 4}, {"xs", s.xs, BT * 8}, {"ys", s.ys, BT * 8}, {"xi", s.xi, BT * 8},
         {"yi", s.yi, BT * 8}, {"cs", s.cs, B * 16}};

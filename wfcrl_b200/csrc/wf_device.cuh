@@ -44,6 +44,13 @@ struct WfState {
     int* episode;       // [B] number of library-sampled resets so far (counter word of the reset sampler)
     uint8_t* amb;       // [B] FP32 kernel: 1 = a discrete decision of this solve was within the guard band of its threshold
                         //     AND could change the result (the env is re-solved by the FP64 kernel), 0 = decisions are safe
+    // episode bookkeeping, advanced by the env-mode epilogue of the step kernels (no host-side mirror, no extra launches):
+    double* ep_return;  // [B] sum of the (shaped) rewards of the running episode
+    int* ep_len;        // [B] its number of steps
+    double* fin_sum;    // [B] over the episodes this env has FINISHED (truncated): sum of returns,
+    double* fin_sumsq;  // [B]   sum of squared returns,
+    int* fin_n;         // [B]   their number,
+    long long* fin_len; // [B]   and the sum of their lengths
     uint8_t* reset_mask;// [B] 1 = the env was reset inside a step kernel and still needs its geometry + warm-up solve
     int* fix_list;      // [B] ids of the envs flagged by the FP32 launches since the last fix-up launch (appended atomically)
     int* fix_count;     // [4 * WF_FIX_SLOTS] per slot: number of flagged envs, number of fix-up CTAs that have left, the

@@ -680,6 +680,7 @@ wf_step_fast_kernel(const int mode, const int env_begin, const int slot, const W
             }
             if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((float*)out.reward)[b] = reward;
+            wfreset::episode_account(s, b, (double)reward, it == m.max_iter);
             s.ws_norm[b] = ws_d;
         }
     }

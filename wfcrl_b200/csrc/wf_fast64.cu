@@ -645,6 +645,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((OutT*)out.reward)[b] = (OutT)reward;
             if (FIX && rec) rec[1] = (float)reward;
+            wfreset::episode_account(s, b, FIX ? (double)(float)reward : reward, it == m.max_iter);  // FIX: what the caller sees
             s.ws_norm[b] = ws;
         }
     }

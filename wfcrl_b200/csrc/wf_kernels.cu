@@ -784,6 +784,7 @@ wf_step_basic_kernel(const int mode, const int env_begin, const WfModel m, const
             }
             if (!isfinite(reward)) s.nonfinite[b] += 1;
             if (out.reward) ((R*)out.reward)[b] = (R)reward;
+            wfreset::episode_account(s, b, (double)(R)reward, it == m.max_iter);
             s.ws_norm[b] = ec.ws;  // next state's freewind measurement (mdp.py:280)
         }
     }

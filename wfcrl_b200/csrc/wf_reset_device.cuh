@@ -66,6 +66,25 @@ __device__ __forceinline__ void reset_scalars(const WfState& s, int b, double ws
     // WindFarmEnv.reset calls reward_shaper.reset(), and StepPercentage.reset() puts its reference back to 0.0 whatever
     // the constructor argument was (rewards.py:45-46): the first shaped reward of every episode is 0
     s.shaper_ref[b] = 0.0;
+    s.ep_return[b] = 0.0;                        // an explicit reset abandons the running episode
+    s.ep_len[b] = 0;
+}
+
+// Episode bookkeeping of one env step (one thread): accumulate the reward; a truncating step closes the episode into the env's
+// finished-episode sums (what VecWindFarmEnv.episode_statistics reduces and all-gathers) and starts the next one at zero.
+__device__ __forceinline__ void episode_account(const WfState& s, int b, double reward, bool truncated) {
+    double er = s.ep_return[b] + reward;
+    int el = s.ep_len[b] + 1;
+    if (truncated) {
+        s.fin_sum[b] += er;
+        s.fin_sumsq[b] += er * er;
+        s.fin_n[b] += 1;
+        s.fin_len[b] += el;
+        er = 0.0;
+        el = 0;
+    }
+    s.ep_return[b] = er;
+    s.ep_len[b] = el;
 }
 
 // In-kernel auto-reset of a step kernel (one thread): zero the per-env counters and mark the env; the wind of its next episode

@@ -26,8 +26,13 @@ def gather_episode_stats(returns: torch.Tensor, lengths: torch.Tensor) -> Dict[s
     """All-gather (sum, sum of squares, count, length sum) of finished-episode returns across ranks and reduce them to
     global statistics.  ``returns``/``lengths``: 1-D tensors of this rank's finished episodes (may be empty)."""
     r = returns.double()
-    local = torch.stack([r.sum(), (r * r).sum(), torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device),
-                         lengths.double().sum()])
+    return gather_episode_sums(float(r.sum()), float((r * r).sum()), float(r.numel()), float(lengths.double().sum()),
+                               r.device)
+
+
+def gather_episode_sums(s: float, ss: float, n: float, length_sum: float, device) -> Dict[str, float]:
+    """The same from this rank's four sums (what the step kernels accumulate per env): the job's only collective."""
+    local = torch.tensor([s, ss, n, length_sum], dtype=torch.float64, device=device)
     rank, size = world()
     if size > 1:
         parts = [torch.zeros_like(local) for _ in range(size)]

@@ -110,9 +110,6 @@ class VecWindFarmEnv:
         self.turbulence_intensity_range = turbulence_intensity_range
         self._arm_autoreset()
         self._zeros_bool = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        self.episode_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
-        self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
-        self.finished_returns, self.finished_lengths = [], []
         self._needs_reset = True
 
     def _arm_autoreset(self):
@@ -206,8 +203,6 @@ class VecWindFarmEnv:
         if len(ids) == self.num_envs:
             self._countdowns = []
         self._countdowns = sorted(set(self._countdowns) | {self.max_num_steps - 1})
-        self.episode_returns[idt] = 0
-        self.episode_lengths[idt] = 0
         self._needs_reset = False
         return self._obs(out)
 
@@ -224,52 +219,53 @@ class VecWindFarmEnv:
             row = self._series[self._series_pos]
             self.backend.update_wind(row[:, 0].contiguous(), row[:, 1].contiguous(), host_trig=self.exact_host_trig)
         out = self.backend.step(action)
+        # nothing else per step on this side: episode returns / lengths and the finished-episode sums are kept by the step
+        # kernel's epilogue (state arrays "ep_return", "ep_len", "fin_*"), `truncated` is the kernel's flag viewed as bool
         reward = out["reward"]
-        truncated = out["truncated"].bool()
-        self.episode_returns += reward.double()
-        self.episode_lengths += 1
+        truncated = out["truncated"].view(torch.bool)
         if self.copy_outputs:
-            reward = reward.clone()
+            reward, truncated = reward.clone(), truncated.clone()
             info = {"power": out["power"].clone(), "load": out["load"].clone()}
         else:
             info = {"power": out["power"], "load": out["load"]}
         obs = self._obs(out)
-        if self._tick():
-            self.finished_returns.append(self.episode_returns[truncated].clone())
-            self.finished_lengths.append(self.episode_lengths[truncated].clone())
-            if self.auto_reset:
-                # same-step autoreset: final observation is preserved in info, obs rows of finished envs restart
-                info["final_observation"] = OrderedDict((k, v.clone()) for k, v in obs.items())
-                info["final_info"] = {"power": out["power"].clone(), "load": out["load"].clone()}
-                truncated = truncated.clone()
-                reward = reward.clone()
-                if self._fused_autoreset:
-                    # the step kernel has already reset the truncated envs' state and marked them: wind draw + geometry +
-                    # warm-up solve of the marked envs, no host round trip
-                    out = self.backend.autoreset_finish(self.start_iter + 1)
-                else:  # time series: the wind generator restarts at a random row (interface.py:517)
-                    mask = out["truncated"]
-                    start = torch.randint(0, self._series.shape[0], (self.num_envs,), device=self.device, generator=self._gen)
-                    self._series_pos = torch.where(truncated, start, self._series_pos)
-                    row = self._series[self._series_pos]
-                    out = self.backend.reset_masked(mask.clone(), row[:, 0].contiguous(), row[:, 1].contiguous(),
-                                                    warmup_solves=self.start_iter + 1)
-                obs = self._obs(out)
-                self.episode_returns[truncated] = 0
-                self.episode_lengths[truncated] = 0
+        if self._tick() and self.auto_reset:
+            # same-step autoreset: final observation is preserved in info, obs rows of finished envs restart
+            info["final_observation"] = OrderedDict((k, v.clone()) for k, v in obs.items())
+            info["final_info"] = {"power": out["power"].clone(), "load": out["load"].clone()}
+            truncated = truncated.clone()
+            reward = reward.clone()
+            if self._fused_autoreset:
+                # the step kernel has already reset the truncated envs' state and marked them: wind draw + geometry +
+                # warm-up solve of the marked envs, no host round trip
+                out = self.backend.autoreset_finish(self.start_iter + 1)
+            else:  # time series: the wind generator restarts at a random row (interface.py:517)
+                start = torch.randint(0, self._series.shape[0], (self.num_envs,), device=self.device, generator=self._gen)
+                self._series_pos = torch.where(truncated, start, self._series_pos)
+                row = self._series[self._series_pos]
+                out = self.backend.reset_masked(truncated.view(torch.uint8).clone(), row[:, 0].contiguous(),
+                                                row[:, 1].contiguous(), warmup_solves=self.start_iter + 1)
+            obs = self._obs(out)
         self.last_info = info  # joint (un-split) info of this step, incl. final_observation on auto-reset steps
         return obs, reward, self._zeros_bool, truncated, info
 
-    def episode_statistics(self):
-        """Global statistics of the finished episodes (all-gathered over ranks when torch.distributed is initialised)."""
-        from .dist import gather_episode_stats
+    @property
+    def episode_returns(self):
+        """Return accumulated so far in every env's RUNNING episode (float64 [B], device copy of the kernel's accumulator)."""
+        return torch.as_tensor(self.backend.get_state("ep_return"), device=self.device)
 
-        if self.finished_returns:
-            r, ln = torch.cat(self.finished_returns), torch.cat(self.finished_lengths)
-        else:
-            r = torch.zeros(0, dtype=torch.float64, device=self.device)
-            ln = torch.zeros(0, dtype=torch.long, device=self.device)
-        return gather_episode_stats(r, ln)
+    @property
+    def episode_lengths(self):
+        return torch.as_tensor(self.backend.get_state("ep_len").astype(np.int64), device=self.device)
+
+    def episode_statistics(self):
+        """Global statistics of the finished episodes (all-gathered over ranks when torch.distributed is initialised), from
+        the per-env sums the step kernels keep: (sum, sum of squares, count, length sum)."""
+        from .dist import gather_episode_sums
+
+        g = self.backend.get_state
+        return gather_episode_sums(float(g("fin_sum").sum()), float(g("fin_sumsq").sum()), float(g("fin_n").sum()),
+                                   float(g("fin_len").sum()), self.device)
 
     def close(self):
         self.backend.close()
