@@ -672,7 +672,7 @@ wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, 
 // s.fix_count[2 slot]); launched right behind every FP32 step launch of a strict handle, usually with nothing or a handful of
 // envs to do, so it is built for latency: W warps per env.  The last CTA to leave re-arms the counters.
 template <int W>
-__global__ void __launch_bounds__(32 * W, 1)
+__global__ void __launch_bounds__(32 * W, W == 1 ? 8 : 1)
 wf_fixup64_kernel(const int mode, const int slot, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
                   const WfState s, const WfOutPtrs out, float* __restrict__ rec, const int rec_cap) {
     const int n = *(volatile int*)&s.fix_count[4 * slot];
@@ -711,13 +711,21 @@ static cudaError_t launch_fixup_t(int mode, bool use_vtab, const WfModel& m, con
 
 cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                               const WfOutPtrs& out, int env_count, int slot, float* d_rec, int rec_cap, cudaStream_t stream) {
-    // The launch is latency-bound (a handful of envs, each a sequential sweep over its turbines): 8 warps per env cover 80
-    // targets in ONE fused pass per source; 4 warps (two resident CTAs per SM instead of one) when the farm is small enough
-    // for one pass anyway or the batch is large enough for the flagged envs to outnumber the SMs.
-    const bool wide = m.T > 40 && env_count <= 12288;
-    const int grid = env_count < (wide ? 148 : 296) ? env_count : (wide ? 148 : 296);
-    return wide ? launch_fixup_t<8>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream)
-                : launch_fixup_t<4>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
+    // The launch is latency-bound while the flagged envs (1-2 % of the batch) are fewer than the CTAs the GPU holds at once,
+    // and each env is a sequential sweep over its turbines: W warps per env cover 10 W targets in one fused pass per source.
+    // So: as many warps as the farm can use (T / 10), fewer when the batch is large enough for the flagged envs to outnumber
+    // the resident CTAs (148 at W = 8, 296 at W = 4, 592 at W = 2, 1184 at W = 1 on a B200: 8 warps of ~196 registers per SM).
+    int w = m.T > 40 ? 8 : (m.T > 20 ? 4 : (m.T > 10 ? 2 : 1));
+    const int expected = env_count / 64 + 1;  // ~1.5 % of the envs
+    while (w > 1 && expected > 148 * 8 / w) w >>= 1;
+    const int resident = 148 * 8 / w;  // two ~196-register warps per SM sub-partition = 8 warps per SM
+    const int grid = env_count < resident ? env_count : resident;
+    switch (w) {
+        case 8: return launch_fixup_t<8>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
+        case 4: return launch_fixup_t<4>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
+        case 2: return launch_fixup_t<2>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
+        default: return launch_fixup_t<1>(mode, use_vtab, m, fc, s, out, grid, slot, d_rec, rec_cap, stream);
+    }
 }
 
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
