@@ -246,7 +246,7 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         (rc = dev_alloc(h, &h->d_rws, (size_t)B)) || (rc = dev_alloc(h, &h->d_rwd, (size_t)B)) ||
         (rc = dev_alloc(h, &h->d_rcs, (size_t)2 * B)))
         return fail(rc);
-    if ((rc = dev_alloc(h, &s.tab_lo, BT))) return fail(rc);
+    if ((rc = dev_alloc(h, &s.tab_lo, BT)) || (rc = dev_alloc(h, &s.tab_glo, BT))) return fail(rc);
     // The vortex table trades the V sweep's arithmetic for one streamed read of 36 reals per turbine pair.  Measured on B200
     // (profiles/r2_vortex_table.md): it pays in the FP64 kernels (whose sweep is 3x more expensive), but not in the FP32 kernel,
     // where the instructions that remain are latency-bound and the direct evaluation wins by 6 % -- so an FP32 handle builds
@@ -270,6 +270,10 @@ int wf_create(const WfConfig* cfg, const double* lx, const double* ly, WfHandle*
         if (cfg->precision == WF_PREC_F64) {
             s.vtab64 = (double*)try_alloc(rows_all * 8);
             s.vtab = s.vtab64;
+            // the FP64 step kernel gathers: target-major rows + the (v, w) scratch (WFCRL_B200_NO_GATHER=1: source-major rows
+            // and the scatter form of the kernel, for A/B measurements)
+            if (s.vtab64 && !getenv("WFCRL_B200_NO_GATHER")) s.vwg = (double2*)try_alloc(BT * 9 * sizeof(double2));
+            m.vtab_tmajor = s.vwg != nullptr;
         } else {
             if (m.amb_eps > 0.f) s.vtab64 = (double*)try_alloc(rows_all * 8);
             if (vtab_in_main) s.vtab = try_alloc(rows_all * 4);
@@ -687,7 +691,7 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
     cudaFuncAttributes attr;
     int ctas = 0, thr = (h->model.T + 31) / 32 * 32, sm = 0;
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64) {
-        CUDA_TRY(wf_step_fast64_attributes(h->model, &attr, &ctas, &thr, &sm));
+        CUDA_TRY(wf_step_fast64_attributes(h->model, h->st, &attr, &ctas, &thr, &sm));
     } else if (h->cfg.kernel == WF_KERNEL_FAST) {
         CUDA_TRY(wf_step_fast_attributes(h->fast_baked, h->fast_uses_vtab && h->st.vtab && !h->vtab_stale, h->model, &attr, &ctas, &thr, &sm));
     } else {

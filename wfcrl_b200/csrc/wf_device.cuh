@@ -19,6 +19,7 @@ struct WfModel {
     unsigned long long ar_seed;    //   key of the counter-based wind sampler
     long long ar_offset;           //   global id of env 0 (the sampler's counter word)
     double ar_ti_lo, ar_ti_hi;     //   ambient-TI range drawn at reset (ti_hi <= ti_lo: keep the current value)
+    int vtab_tmajor;               // vortex-table rows are stored target-major (FP64 handle: the gather kernel), else source-major
     float amb_eps;                 // relative half-width of the guard band around the 0.05 m/s overlap threshold (FP32 kernel)
     double load_coef, shaper_reference;
     double rho, ref_rho, shear, D, HH, TSR, pP;
@@ -86,6 +87,12 @@ struct WfState {
     uint8_t* vtab_ok;   // [B] 1 = the env's rows match its current geometry (cleared by the geometry kernel)
     uint8_t* tab_lo;    // [B][T] per sorted source i: first t with xs[t] - xs[i] > 1e-6 m; closer targets (x-ties) are
                         //         evaluated directly from the positions, never through the table
+    uint8_t* tab_glo;   // [B][T] the same relation seen from sorted target t: number of sources j with xs[t] - xs[j] > 1e-6 m
+                        //         (a prefix of the sorted order) = the table sources of t
+    // FP64 gather kernel (target-major table, m.vtab_tmajor): row(j, t) of source j < target t at index t*(t-1)/2 + j, so
+    // that the rows one target sums in its prologue are contiguous; the finished (v, w) of every rotor point and the direct
+    // contributions between x-tied turbines live in this scratch (rewritten by every launch; L2-resident while an env runs)
+    double2* vwg;       // [B][9T] or NULL
 };
 
 // Constants of the tuned warp-per-env kernels, precomputed on the host in FP64 (wf_host_const.h: build_fast_const);
@@ -158,5 +165,5 @@ cudaError_t wf_step_fast_attributes(bool baked, bool use_vtab, const WfModel& m,
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                   const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream);
-cudaError_t wf_step_fast64_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+cudaError_t wf_step_fast64_attributes(const WfModel& m, const WfState& s, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                       int* smem);

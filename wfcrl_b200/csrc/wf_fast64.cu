@@ -23,6 +23,12 @@
 #define WF_VTAB64_PF_DIST 1  // table rows of source i + 1 are prefetched to L2 while source i is processed (2: -4 %, 4: -8 %)
 #endif
 
+#ifndef WF_GATHER_PF_DIST
+#define WF_GATHER_PF_DIST 1  // gather kernel: rows of target i + 1 are prefetched to L2 while source i is processed (measured at
+                             // 8192 x 80: none 2.25 M env-steps/s, 1: 2.31 M, 2: 2.10 M with 12.4 GB instead of 8.6 GB read from HBM,
+                             // the lines of 2072 resident envs x 2 targets no longer survive in L2 until their use)
+#endif
+
 namespace {
 
 constexpr double kPi = 3.141592653589793;
@@ -37,6 +43,13 @@ __device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int
     const char* p = (const char*)env_rows + ((size_t)i * T - (size_t)i * (i + 1) / 2) * row_bytes;
     const unsigned bytes = (unsigned)(T - 1 - i) * row_bytes;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// target-major table (gather kernel): the rows (j, t) of the table sources j < n_rows of sorted target `t` are contiguous
+__device__ __forceinline__ void prefetch_target_rows64(const void* env_rows, int t, int n_rows, int lane) {
+    if (n_rows <= 0 || lane != 0) return;
+    const char* p = (const char*)env_rows + ((size_t)t * (t - 1) / 2) * 288;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)n_rows * 288u) : "memory");
 }
 
 // ---- lean double-precision primitives for the solver's critical path ----------------------------------------------------
@@ -95,7 +108,9 @@ __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double
 }
 
 struct SmemView64 {
-    double2* vw;              // [9T] (v, w) per rotor point
+    double2* vw;              // [9T] (v, w) per rotor point (scatter kernels; the gather kernel keeps them in s.vwg)
+    double2* gg;              // [T] (Gt, Gwr) of the sources processed so far (gather kernel)
+    double2* red;             // [96] per-lane partial sums of the gather
     double* wsq;              // [9T] running sum of squared deficits
     double *xs, *ys;          // [T] sorted rotated coordinates (the sources' grid means x_i, y_i are read from global memory)
     double* tia;              // [3T]
@@ -107,9 +122,9 @@ struct SmemView64 {
     unsigned char* queue;     // [T]
 };
 
-__host__ __device__ inline size_t fast64_smem_bytes(int T) {
+__host__ __device__ inline size_t fast64_smem_bytes(int T, bool gather = false) {
     size_t n = 0;
-    n += (size_t)9 * T * 16;  // vw
+    n += gather ? (size_t)T * 16 + 96 * 16 : (size_t)9 * T * 16;  // gg + red, or vw
     n += (size_t)9 * T * 8;   // wsq
     n += (size_t)2 * T * 8;   // xs, ys
     n += (size_t)3 * T * 8;   // tia
@@ -119,10 +134,12 @@ __host__ __device__ inline size_t fast64_smem_bytes(int T) {
     return (n + 15) / 16 * 16;
 }
 
-__device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T) {
+__device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T, bool gather) {
     SmemView64 s;
     s.vw = (double2*)base;
-    double* f = (double*)(s.vw + 9 * T);
+    s.gg = (double2*)base;
+    s.red = s.gg + T;
+    double* f = gather ? (double*)(s.red + 96) : (double*)(s.vw + 9 * T);
     s.wsq = f; f += 9 * T;
     s.xs = f; f += T;
     s.ys = f; f += T;
@@ -147,9 +164,15 @@ __device__ __forceinline__ void load_row12(const double* __restrict__ p, double*
 //   W = 1: the throughput configuration of the bit-check mode (one warp = one CTA = one env, compacted deficit queue).
 //   W > 1: the low-latency configuration used to re-solve the envs an FP32 launch flagged: every warp evaluates the source's
 //          scalar chain itself (no broadcast), then the W warps share the targets of ONE fused vortex + deficit pass.
+// GATHER (W = 1 with a target-major vortex table): the (v, w) of a turbine are not accumulated in shared memory while the
+//          upstream sources are processed but summed from the table rows (j, i), j < i, in the prologue of source i, with the
+//          circulations (Gt, Gwr) of the earlier sources kept in shared memory (16 bytes per turbine instead of 144); the
+//          finished values -- and the contributions exchanged between x-tied turbines, evaluated directly -- live in the
+//          global scratch s.vwg (L2-resident).  Shared memory per env drops from 23.5 KB to 15 KB at 80 turbines, which lets
+//          12 envs share an SM instead of 9.
 // OutT = type of the caller's output buffers (double for an FP64 handle, float for the re-solve on an FP32 handle).  FIX = re-solve: the FP32 kernel has already applied the action (yaw and
 // accumulators are committed) but none of the per-env epilogue state, which is committed here.
-template <int W, typename OutT, bool FIX>
+template <int W, typename OutT, bool FIX, bool GATHER = false>
 __device__ __forceinline__ void solve_env64(const int b, const int mode, const bool use_vtab, const WfModel& m,
                                             const WfFastConst64& fc, const WfState& s, const float* __restrict__ action,
                                             const double* __restrict__ yaw_cmd, const WfOutPtrs& out,
@@ -160,7 +183,16 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     auto csync = [] { if (W == 1) __syncwarp(); else __syncthreads(); };
     const size_t row = (size_t)b * T;
     extern __shared__ __align__(16) unsigned char smem_raw64[];
-    const SmemView64 sm = carve64(smem_raw64, T);
+    static_assert(!GATHER || W == 1, "the gather form is the one-warp throughput kernel");
+    const SmemView64 sm = carve64(smem_raw64, T, GATHER);
+    // (v, w) per rotor point: shared memory, or the env's global scratch (cache-global accesses: lanes exchange values
+    // through it between __syncwarp()s)
+    double2* const vwp = GATHER ? s.vwg + (size_t)b * 9 * T : sm.vw;
+    auto vw_ld = [&](const int q) -> double2 { return GATHER ? __ldcg(vwp + q) : vwp[q]; };
+    auto vw_st = [&](const int q, const double2 v) { if (GATHER) __stcg(vwp + q, v); else vwp[q] = v; };
+    // vortex table of this env (wf_device.cuh), or NULL: evaluate every pair directly
+    const double* __restrict__ vrow = nullptr;
+    if (use_vtab && s.vtab64 && s.vtab_ok[b] && (GATHER || !m.vtab_tmajor)) vrow = s.vtab64 + (size_t)b * ((size_t)T * (T - 1) / 2) * 36;
 
     // ---- env prologue on the ORIGINAL turbine order (mdp.py:291-319, simple_env.py:64-72) -------------------------
     int nm = 0;
@@ -193,7 +225,17 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         sm.idx[tt] = s.idx[row + tt];
         sm.ordr[tt] = (unsigned char)s.order[row + tt];
     }
-    for (int q = tid; q < 9 * T; q += NT) { sm.wsq[q] = 0.0; sm.vw[q] = make_double2(0.0, 0.0); }
+    for (int q = tid; q < 9 * T; q += NT) {
+        sm.wsq[q] = 0.0;
+        if (!GATHER) sm.vw[q] = make_double2(0.0, 0.0);
+    }
+    if (GATHER) {  // scratch entries of the turbines that exchange direct (x-tie) contributions start from zero
+        for (int tt = tid; tt < T; tt += NT) {
+            const bool tied = !vrow || (int)s.tab_glo[row + tt] < tt || (int)s.tab_lo[row + tt] > tt + 1;
+            if (tied)
+                for (int p = 0; p < 9; ++p) __stcg(vwp + 9 * tt + p, make_double2(0.0, 0.0));
+        }
+    }
     for (int q = tid; q < 3 * T; q += NT) sm.tia[q] = 0.0;
     csync();
     for (int tt = tid; tt < T; tt += NT) {
@@ -223,21 +265,68 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     const double cwl0 = fc.cw[0][plc], cwl1 = fc.cw[1][plc], cwl2 = fc.cw[2][plc];
     const double c_dec = fc.eps2 * fc.inv_2pi;
     const double eps2 = fc.eps2;
-    // vortex table of this env (wf_device.cuh), or NULL: evaluate every pair directly
-    const double* __restrict__ vrow = nullptr;
-    if (use_vtab && s.vtab64 && s.vtab_ok[b]) vrow = s.vtab64 + (size_t)b * ((size_t)T * (T - 1) / 2) * 36;
     if (vrow && warp == 0) {
 #pragma unroll
-        for (int d = 0; d < WF_VTAB64_PF_DIST; ++d) prefetch_rows64(vrow, d, T, lane, 288);
+        if (GATHER) {
+            for (int tt = 1; tt < WF_GATHER_PF_DIST && tt < T; ++tt) prefetch_target_rows64(vrow, tt, (int)s.tab_glo[row + tt], lane);
+        } else {
+            for (int d = 0; d < WF_VTAB64_PF_DIST; ++d) prefetch_rows64(vrow, d, T, lane, 288);
+        }
     }
 
     for (int i = 0; i < T; ++i) {
-        if (vrow && warp == 0) prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
+        if (vrow && warp == 0) {
+            if (GATHER) {
+                const int tn = i + WF_GATHER_PF_DIST;
+                if (WF_GATHER_PF_DIST > 0 && tn < T) prefetch_target_rows64(vrow, tn, (int)s.tab_glo[row + tn], lane);
+            } else {
+                prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
+            }
+        }
         // ===== source prologue (every warp on its own: all values below are block-uniform) =====
         double su3, sv, sw, vq, wwq;
         {
             const double wq = sm.wsq[9 * i + plc];
-            const double2 vw0 = sm.vw[9 * i + plc];
+            double2 vw0;
+            if (GATHER) {
+                // table sources of this turbine: the sorted prefix [0, glo); the x-tied ones in [glo, i) have added
+                // their part to the scratch entry directly
+                const int glo = vrow ? (int)__ldg(s.tab_glo + row + i) : 0;
+                vw0 = (glo < i) ? __ldcg(vwp + 9 * i + plc) : make_double2(0.0, 0.0);
+                if (glo > 0) {
+                    double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+                    const double* __restrict__ trow = vrow + ((size_t)i * (i - 1) / 2) * 36 + 12 * j;
+#pragma unroll 2
+                    for (int j0 = 0; j0 < glo; j0 += kTurbPerPass) {
+                        const int jj = j0 + g;
+                        if (lane_ok && jj < glo) {
+                            double c[12];
+                            load_row12(trow + (size_t)jj * 36, c);
+                            const double2 G = sm.gg[jj];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                acc[k].x += G.x * c[4 * k] + G.y * c[4 * k + 1];
+                                acc[k].y += fmax(G.x * c[4 * k + 2] + G.y * c[4 * k + 3], 0.0);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sm.red[3 * lane + k] = acc[k];
+                    __syncwarp();
+                    const int rb = plc;  // lane 3 g' + column wrote [k] at 9 g' + 3 column + k = 9 g' + rotor point
+                    double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int gq = 0; gq < kTurbPerPass; ++gq) {
+                        const double2 e = sm.red[9 * gq + rb];
+                        sum.x += e.x;
+                        sum.y += e.y;
+                    }
+                    vw0.x += sum.x;
+                    vw0.y += sum.y;
+                }
+            } else {
+                vw0 = sm.vw[9 * i + plc];
+            }
             vq = vw0.x;
             wwq = vw0.y;
             const double u = U0p - sqrt64z(wq);
@@ -344,8 +433,11 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
             sumW += rw;
             csync();  // every reader of this turbine's (v, w) above is done (self_on is block-uniform)
-            if (tid < 9) sm.vw[9 * i + tid] = make_double2(vq + Vs, wwq + Ws);
+            if (tid < 9) vw_st(9 * i + tid, make_double2(vq + Vs, wwq + Ws));
+        } else if (GATHER) {
+            if (tid < 9) vw_st(9 * i + tid, make_double2(vq, wwq));
         }
+        if (GATHER && tid == 0) sm.gg[i] = make_double2(Gt, Gwr);
         const double aI = avg * tp0;
         const double kk2 = 3.0 * aI * aI;
         const double v_term = sumV * (1.0 / 9.0), w_term = sumW * (1.0 / 9.0);
@@ -405,13 +497,14 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 const int qb = 9 * t + 3 * j;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const double2 o = sm.vw[qb + k];
-                    sm.vw[qb + k] = make_double2(o.x + Vk[k], o.y + Wk[k]);
+                    const double2 o = vw_ld(qb + k);
+                    vw_st(qb + k, make_double2(o.x + Vk[k], o.y + Wk[k]));
                 }
             }
         };
         // --- the same through the table row of the sorted pair (i, t): V += Gt*cVt + Gwr*cVw ; W += max(Gt*cWt + Gwr*cWw, 0)
         auto v_table = [&](const int t, const bool active) {
+            if (GATHER) return;  // (the gather kernel reads the table in the target's prologue)
             double c[12];
             load_row12(vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2 + (size_t)(t - i - 1)) * 36 + 12 * j, c);
             if (active) {
@@ -475,7 +568,42 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         auto reach = [&](const double dx) { return reach1 * dx + reach0 + fabs(fc.bd * dx + fc.ad); };
         const int t_hi = vrow ? (int)s.tab_lo[row + i] : T;  // with the table only the x-ties take the direct path
 
-        if (W == 1) {
+        if (W == 1 && GATHER) {
+            // ===== direct (v, w) exchange with the x-tied turbines, queue of the targets within reach of the wake (32
+            //       candidates per pass), D sweep over the queue =====
+#pragma unroll 1
+            for (int t0 = lo; t0 < ((t_hi - lo > 1 || !vrow) ? t_hi : lo); t0 += kTurbPerPass) {  // without ties [lo, t_hi) = {i}
+                const int tr = t0 + g;
+                const bool active = lane_ok && tr < t_hi && tr != i;
+                const int t = min(tr, T - 1);
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                v_direct(t, dx, dyc, active);
+            }
+            int qn = 0;
+#pragma unroll 1
+            for (int t0 = near_i; t0 < T; t0 += 32) {
+                const int tr = t0 + lane;
+                const int t = min(tr, T - 1);
+                const double r = reach(sm.xs[t] - x_i), yt = sm.ys[t];
+                const bool need = tr < T && (fabs(__dsub_rn(__dadd_rn(yt, fc.offj[0]), y_i)) < r ||
+                                             fabs(__dsub_rn(__dadd_rn(yt, fc.offj[1]), y_i)) < r ||
+                                             fabs(__dsub_rn(__dadd_rn(yt, fc.offj[2]), y_i)) < r);
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                if (need) sm.queue[qn + __popc(nb & ((1u << lane) - 1u))] = (unsigned char)t;
+                qn += __popc(nb);
+            }
+            __syncwarp();
+            for (int q0 = 0; q0 < qn; q0 += kTurbPerPass) {
+                const int e = q0 + g;
+                const bool active = lane_ok && e < qn;
+                const int t = sm.queue[min(e, qn - 1)];
+                const double dx = sm.xs[t] - x_i;
+                const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
+                d_apply(t, dx, dyc, active);
+            }
+            __syncwarp();
+        } else if (W == 1) {
             // ===== V sweep over all downstream targets (builds the compacted queue), then D sweep over the queue =====
             int qn = 0;
             auto enqueue = [&](const int t, const bool need) {
@@ -552,9 +680,9 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         for (int p = 0; p < 9; ++p) {
             const double U0k = (p % 3 == 0) ? U0a : ((p % 3 == 1) ? U0b : U0c);
             u[p] = U0k - sqrt(sm.wsq[9 * tt + p]);
-            const double2 vwp = sm.vw[9 * tt + p];
-            vv[p] = vwp.x;
-            ww[p] = vwp.y;
+            const double2 vwe = vw_ld(9 * tt + p);
+            vv[p] = vwe.x;
+            ww[p] = vwe.y;
             c3[p] = u[p] * u[p] * u[p];
             dd[p] = wd - kDeg * atan2(vv[p], u[p]);
         }
@@ -657,15 +785,21 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     }
 }
 
-// 12 CTAs per SM: the register file is split over the 4 SM sub-partitions (16 K registers each), so a one-warp CTA needs
-// <= 168 registers for three of them to share a sub-partition (192 would leave two: 8 per SM)
-__global__ void __launch_bounds__(32, 12)
+// The register file is split over the 4 SM sub-partitions (16 K registers each): a one-warp CTA of <= 168 registers shares a
+// sub-partition with two others (12 per SM), one of 128 registers with three (16 per SM; 12-48 bytes of spills).  The kernels
+// are latency-bound, throughput grows with the resident envs (measured on Turb32_Row5: 6 per SM 4.9 M env-steps/s, 9: 6.2 M,
+// 12: 7.6 M, 16: 8.2 M); at 80 turbines shared memory holds 14 envs of the gather kernel per SM (9 of the scatter kernel).
+#ifndef WF_FAST64_GATHER_MINB
+#define WF_FAST64_GATHER_MINB 16
+#endif
+template <bool GATHER>
+__global__ void __launch_bounds__(32, WF_FAST64_GATHER_MINB)
 wf_step_fast64_kernel(const int mode, const int env_begin, const bool use_vtab, const WfModel m, const __grid_constant__ WfFastConst64 fc,
                       const WfState s, const uint8_t* __restrict__ mask, const float* __restrict__ action,
                       const double* __restrict__ yaw_cmd, const WfOutPtrs out) {
     const int b = blockIdx.x + env_begin;
     if (mask && !mask[b]) return;
-    solve_env64<1, double, false>(b, mode, use_vtab, m, fc, s, action, yaw_cmd, out);
+    solve_env64<1, double, false, GATHER>(b, mode, use_vtab, m, fc, s, action, yaw_cmd, out);
 }
 
 // Re-solve, in FP64, of the envs an FP32 launch flagged (their ids sit in s.fix_list[env_begin ...], their number in
@@ -728,35 +862,51 @@ cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const W
     }
 }
 
+static bool fast64_gathers(const WfModel& m, const WfState& s) { return m.vtab_tmajor && s.vtab64 && s.vwg && s.tab_glo; }
+template <typename K> static cudaError_t configure_fast64(K kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t wf_launch_step_fast64(int mode, bool use_vtab, const WfModel& m, const WfFastConst64& fc, const WfState& s,
                                   const uint8_t* d_mask, const float* d_action, const double* d_yaw_cmd,
                                   const WfOutPtrs& out, int env_begin, int env_count, cudaStream_t stream) {
-    const size_t smem = fast64_smem_bytes(m.T);
+    // a target-major table (and its scratch) belongs to the gather kernel; the scatter kernel reads a source-major one or
+    // evaluates every pair directly
+    const bool gather = fast64_gathers(m, s) && use_vtab;
+    size_t smem = fast64_smem_bytes(m.T, gather);
+#ifdef WF_EXP_SMEM_PAD
+    if (const char* e = getenv("WFCRL_B200_F64_SMEM_PAD")) smem += (size_t)atoi(e);
+#endif
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
+        cudaError_t e = configure_fast64(wf_step_fast64_kernel<false>);
+        if (e == cudaSuccess) e = configure_fast64(wf_step_fast64_kernel<true>);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    wf_step_fast64_kernel<<<env_count, 32, smem, stream>>>(mode, env_begin, use_vtab, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    if (gather)
+        wf_step_fast64_kernel<true><<<env_count, 32, smem, stream>>>(mode, env_begin, true, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
+    else
+        wf_step_fast64_kernel<false><<<env_count, 32, smem, stream>>>(mode, env_begin, use_vtab, m, fc, s, d_mask, d_action, d_yaw_cmd, out);
     return cudaGetLastError();
 }
 
-cudaError_t wf_step_fast64_attributes(const WfModel& m, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
+cudaError_t wf_step_fast64_attributes(const WfModel& m, const WfState& s, cudaFuncAttributes* attr, int* ctas_per_sm, int* threads,
                                       int* smem) {
     *threads = 32;
-    *smem = (int)fast64_smem_bytes(m.T);
-    cudaError_t e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const bool gather = fast64_gathers(m, s);
+    *smem = (int)fast64_smem_bytes(m.T, gather);
+#ifdef WF_EXP_SMEM_PAD
+    if (const char* e = getenv("WFCRL_B200_F64_SMEM_PAD")) *smem += atoi(e);
+#endif
+    cudaError_t e = gather ? configure_fast64(wf_step_fast64_kernel<true>) : configure_fast64(wf_step_fast64_kernel<false>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(wf_step_fast64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    e = gather ? cudaFuncGetAttributes(attr, wf_step_fast64_kernel<true>) : cudaFuncGetAttributes(attr, wf_step_fast64_kernel<false>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(attr, wf_step_fast64_kernel);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast64_kernel, 32, *smem);
+    return gather ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast64_kernel<true>, 32, *smem)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, wf_step_fast64_kernel<false>, 32, *smem);
 }

@@ -250,9 +250,10 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
         const double x_i = s.xi[o];
         const double x01 = __dadd_rn(x_i, 0.1), x15 = __dadd_rn(15 * m.D, x_i);
         const double xtie = __dadd_rn(xsrt[t], 1e-6);
-        int i0 = T, i1 = T, i2 = T, i3 = T, i4 = T;
+        int i0 = T, i1 = T, i2 = T, i3 = T, i4 = T, i5 = 0;
         for (int q = T - 1; q >= 0; --q) {
             const double xq = xsrt[q];
+            i5 += xsrt[t] > __dadd_rn(xq, 1e-6);  // q's tab_lo <= t
             if (__dsub_rn(xq, x_i) >= 0.0) i0 = q;
             if (xq > x01) i1 = q;
             if (xq > x_i) i2 = q;
@@ -261,6 +262,7 @@ wf_geometry_kernel(const WfModel m, const WfState s, const uint8_t* __restrict__
         }
         s.idx[o] = make_uchar4((unsigned char)i0, (unsigned char)i1, (unsigned char)i2, (unsigned char)i3);
         s.tab_lo[o] = (unsigned char)i4;
+        s.tab_glo[o] = (unsigned char)i5;
     }
     if (t == 0 && s.vtab_ok) s.vtab_ok[b] = 0;  // the vortex table of this env no longer matches its geometry
 }
@@ -306,7 +308,7 @@ wf_vortex_table_kernel(const WfModel m, const __grid_constant__ WfFastConst64 fc
         const double yL = dyc + kNumEps;
         const double q = yL * yL;
         const double E = exp(-q * fc.inv_eps2);
-        const size_t dst = (size_t)row * 36 + j * 12;
+        const size_t dst = (m.vtab_tmajor ? (size_t)(t * (t - 1) / 2 + i) : (size_t)row) * 36 + j * 12;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             double A[3], Bc[3];  // per unit circulation of (top pair, bottom pair, wake-rotation pair): V and W sums
