@@ -609,8 +609,9 @@ def run_ours(args):
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "path": "FlorisBatch.step_host -> wf_step_host (pinned HOST action in, full step result out): "
-                            "6 env chunks, one stream each, H2D + FP32 kernel + D2H per chunk, then ONE FP64 re-solve launch "
-                            "whose envs come back as compact records scattered into the caller's arrays",
+                            "6 env chunks, one stream each, H2D + step kernel + D2H per chunk" +
+                            (", then ONE FP64 re-solve launch whose envs come back as compact records scattered into the "
+                             "caller's arrays" if precision == "f32" else ""),
                     "host_numa_binding": numa,
                     "observation_only_value": world * B * e2e_steps / e2e_obs_s,
                     "observation_only_d2h_bytes_per_step": int(d2h_obs),
