@@ -23,12 +23,6 @@
 #define WF_VTAB64_PF_DIST 1  // table rows of source i + 1 are prefetched to L2 while source i is processed (2: -4 %, 4: -8 %)
 #endif
 
-#ifndef WF_GATHER_PF_DIST
-#define WF_GATHER_PF_DIST 1  // gather kernel: rows of target i + 1 are prefetched to L2 while source i is processed (measured at
-                             // 8192 x 80: none 2.25 M env-steps/s, 1: 2.31 M, 2: 2.10 M with 12.4 GB instead of 8.6 GB read from HBM,
-                             // the lines of 2072 resident envs x 2 targets no longer survive in L2 until their use)
-#endif
-
 namespace {
 
 constexpr double kPi = 3.141592653589793;
@@ -267,22 +261,12 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     const double eps2 = fc.eps2;
     if (vrow && warp == 0) {
 #pragma unroll
-        if (GATHER) {
-            for (int tt = 1; tt < WF_GATHER_PF_DIST && tt < T; ++tt) prefetch_target_rows64(vrow, tt, (int)s.tab_glo[row + tt], lane);
-        } else {
+        if (!GATHER)
             for (int d = 0; d < WF_VTAB64_PF_DIST; ++d) prefetch_rows64(vrow, d, T, lane, 288);
-        }
     }
 
     for (int i = 0; i < T; ++i) {
-        if (vrow && warp == 0) {
-            if (GATHER) {
-                const int tn = i + WF_GATHER_PF_DIST;
-                if (WF_GATHER_PF_DIST > 0 && tn < T) prefetch_target_rows64(vrow, tn, (int)s.tab_glo[row + tn], lane);
-            } else {
-                prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
-            }
-        }
+        if (!GATHER && vrow && warp == 0) prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
         // ===== source prologue (every warp on its own: all values below are block-uniform) =====
         double su3, sv, sw, vq, wwq;
         {
@@ -580,6 +564,11 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
                 v_direct(t, dx, dyc, active);
             }
+            // The table rows of the NEXT target are pulled into L2 now, one deficit sweep ahead of their use.  Measured at
+            // 8192 x 80 (profiles/r2_exp_gather_prefetch.log): no prefetch 2.25 M env-steps/s; here 2.36 M (7.6 GB read from HBM
+            // per launch = the table once); at the top of the iteration 2.31 M (8.6 GB); one iteration earlier still 2.10 M
+            // (12.4 GB: with 2072 resident envs the prefetched lines no longer survive in L2 until they are used).
+            if (vrow && i + 1 < T) prefetch_target_rows64(vrow, i + 1, (int)s.tab_glo[row + i + 1], lane);
             int qn = 0;
 #pragma unroll 1
             for (int t0 = near_i; t0 < T; t0 += 32) {
