@@ -30,6 +30,7 @@ constexpr double kDeg = 180.0 / kPi;
 constexpr double kRad = kPi / 180.0;
 constexpr double kNumEps = 0.001;
 constexpr int kTurbPerPass = 10;
+constexpr int kSrcPar = 24;  // doubles per source handed from the chain warp to the worker warps (solve_env64, W > 1)
 
 // see wf_fast.cu: pull the vortex-table rows of sorted source `i` into L2 ahead of their use (one bulk prefetch)
 __device__ __forceinline__ void prefetch_rows64(const void* env_rows, int i, int T, int lane, unsigned row_bytes) {
@@ -46,6 +47,13 @@ __device__ __forceinline__ void prefetch_target_rows64(const void* env_rows, int
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)n_rows * 288u) : "memory");
 }
 
+// named barriers (ids 1 .. 15; 0 is __syncthreads): the producer side arrives, the consumer side waits; `count` = all threads
+// taking part on either side.  Ids are immediates (a register id makes ptxas reserve all 16 barriers for the CTA).
+template <int ID> __device__ __forceinline__ void bar_arrive_c(int count) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory"); }
+template <int ID> __device__ __forceinline__ void bar_sync_c(int count) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory"); }
+template <int BASE> __device__ __forceinline__ void bar_arrive(int parity, int count) { if (parity & 1) bar_arrive_c<BASE + 1>(count); else bar_arrive_c<BASE>(count); }
+template <int BASE> __device__ __forceinline__ void bar_sync(int parity, int count) { if (parity & 1) bar_sync_c<BASE + 1>(count); else bar_sync_c<BASE>(count); }
+
 // ---- lean double-precision primitives for the solver's critical path ----------------------------------------------------
 // The FP64 kernels are bound by the LATENCY of one warp's chain of dependent double-precision operations, and the library
 // division / sqrt / cbrt (IEEE rounding, full range, special cases) are 15-50 dependent instructions each.  The quantities
@@ -59,7 +67,6 @@ __device__ __forceinline__ double rcp64(double b) {
     r = fma(r, fma(-b, r, 1.0), r);  // -> rounding
     return r;
 }
-__device__ __forceinline__ double div64(double a, double b) { return a * rcp64(b); }
 __device__ __forceinline__ double sqrt64(double x) {  // x > 0
     float rf;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
@@ -97,7 +104,7 @@ __device__ __forceinline__ double interp_d(const WfFastConst64& fc, const double
     while (idx + 1 < n - 1 && fc.tab_ws[idx + 1] <= x) ++idx;
     const double xa = fc.tab_ws[idx], fa = fp[idx];
     if (x == xa) return fa;
-    const double slope = (fp[idx + 1] - fa) / (fc.tab_ws[idx + 1] - xa);
+    const double slope = (fp[idx + 1] - fa) * rcp64(fc.tab_ws[idx + 1] - xa);  // (table nodes are >= 0.01 m/s apart)
     return slope * (x - xa) + fa;
 }
 
@@ -114,6 +121,8 @@ struct SmemView64 {
     uchar4* idx;              // [T]
     unsigned char* ordr;      // [T]
     unsigned char* queue;     // [T]
+    double* spar;             // [2][3][kSrcPar] scatter kernels: the source parameters, per lateral column, that the chain
+                              // warp hands to the worker warps (double-buffered over the parity of the source index)
 };
 
 __host__ __device__ inline size_t fast64_smem_bytes(int T, bool gather = false) {
@@ -125,7 +134,9 @@ __host__ __device__ inline size_t fast64_smem_bytes(int T, bool gather = false) 
     n += (size_t)4 * T * 8;   // cyaw, syaw, tifin, ynew
     n += (size_t)T * 4;       // idx
     n += (size_t)2 * ((T + 15) / 16 * 16);
-    return (n + 15) / 16 * 16;
+    n = (n + 15) / 16 * 16;
+    if (!gather) n += 2 * 3 * kSrcPar * 8;  // spar
+    return n;
 }
 
 __device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T, bool gather) {
@@ -145,6 +156,7 @@ __device__ __forceinline__ SmemView64 carve64(unsigned char* base, int T, bool g
     s.idx = (uchar4*)f;
     s.ordr = (unsigned char*)(s.idx + T);
     s.queue = s.ordr + (T + 15) / 16 * 16;
+    s.spar = (double*)(base + fast64_smem_bytes(T, gather) - 2 * 3 * kSrcPar * 8);  // (not touched by the gather kernel)
     return s;
 }
 
@@ -260,14 +272,30 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
     const double c_dec = fc.eps2 * fc.inv_2pi;
     const double eps2 = fc.eps2;
     if (vrow && warp == 0) {
-#pragma unroll
         if (!GATHER)
             for (int d = 0; d < WF_VTAB64_PF_DIST; ++d) prefetch_rows64(vrow, d, T, lane, 288);
     }
 
+    // W > 1, chain warp: the transverse velocities source i - 1 induces on turbine i are not written to shared memory but added
+    // in registers at the head of source i's prologue, from table coefficients loaded one source earlier (no load latency on
+    // the chain); per lane: rotor point plc of the pair (i - 1, i)
+    double near_gt = 0.0, near_gwr = 0.0;
+    double2 near_c0 = make_double2(0.0, 0.0), near_c1 = make_double2(0.0, 0.0);
+    bool near_tab = false;
     for (int i = 0; i < T; ++i) {
         if (!GATHER && vrow && warp == 0) prefetch_rows64(vrow, i + WF_VTAB64_PF_DIST, T, lane, 288);
-        // ===== source prologue (every warp on its own: all values below are block-uniform) =====
+        double2 next_c0 = make_double2(0.0, 0.0), next_c1 = make_double2(0.0, 0.0);
+        bool next_tab = false;
+        if (W > 1 && warp == 0 && vrow && i + 1 < T && i + 1 >= (int)s.tab_lo[row + i]) {
+            next_tab = true;
+            const double2* r = (const double2*)(vrow + ((size_t)i * T - (size_t)i * (i + 1) / 2) * 36 + 12 * (plc / 3) + 4 * (plc % 3));
+            next_c0 = __ldg(r);
+            next_c1 = __ldg(r + 1);
+        }
+        // ===== source prologue: the scalar chain of source i.  W == 1: the one warp does everything.  W > 1: warp 0 (the chain
+        //       warp) evaluates it and hands the parameters of the sweeps to the worker warps through shared memory =====
+        double par[kSrcPar];
+        if (W == 1 || warp == 0) {
         double su3, sv, sw, vq, wwq;
         {
             const double wq = sm.wsq[9 * i + plc];
@@ -310,6 +338,10 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
                 }
             } else {
                 vw0 = sm.vw[9 * i + plc];
+                if (W > 1 && near_tab) {
+                    vw0.x += near_gt * near_c0.x + near_gwr * near_c0.y;
+                    vw0.y += fmax(near_gt * near_c1.x + near_gwr * near_c1.y, 0.0);
+                }
             }
             vq = vw0.x;
             wwq = vw0.y;
@@ -416,9 +448,9 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
 #pragma unroll
             for (int sft = 8; sft > 0; sft >>= 1) rw += __shfl_xor_sync(0xffffffffu, rw, sft);
             sumW += rw;
-            csync();  // every reader of this turbine's (v, w) above is done (self_on is block-uniform)
+            __syncwarp();  // every reader of this turbine's (v, w) above is done
             if (tid < 9) vw_st(9 * i + tid, make_double2(vq + Vs, wwq + Ws));
-        } else if (GATHER) {
+        } else if (GATHER || (W > 1 && near_tab)) {
             if (tid < 9) vw_st(9 * i + tid, make_double2(vq, wwq));
         }
         if (GATHER && tid == 0) sm.gg[i] = make_double2(Gt, Gwr);
@@ -440,19 +472,48 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
         const double sy0v = sz0v * cy;
         const double near_s = fc.near_c * sM0;
         const double ctc = ct * cy * fc.d2_8;
+        // Crespo-Hernandez constant ch_const a^ai I0^init.  W > 1: only the deficit sweeps need it, so the chain warp hands over
+        // `a` and the power is taken where a sweep finds a target within reach (off the chain's critical path)
 #ifdef WF_DBG_SKIP_POW  // timing experiment only
         const double watK = fc.ch_const * a * I0p;
 #else
-        const double watK = fc.ch_const * exp(fc.ch_ai * log(a)) * I0p;  // a^ai (pow(): 3x the instructions, same to 1e-15)
+        const double watK = (W == 1) ? fc.ch_const * exp(fc.ch_ai * log(a)) * I0p : a;  // a^ai (pow(): 3x the instructions, same to 1e-15)
 #endif
-
-        const int lo = ix.x, near_i = ix.y, gt0_i = ix.z, end15 = ix.w;
-        const double x_i = __ldg(s.xi + row + i), y_i = __ldg(s.yi + row + i);  // block-uniform, L1-resident
 
         constexpr double kCut = 9.5;
         const double reach1 = kCut * kyv;
         // (a conservative cut-off: single precision is plenty for the logarithm)
         const double reach0 = kCut * fmax(near_s, sy0v) + fabs(delta0) + fabs(Kck) * (double)(__logf((float)A_ln) * 1.0001f);
+        par[0] = Gt; par[1] = Gb; par[2] = Gwr; par[3] = x0d; par[4] = inv_x0d; par[5] = delta0; par[6] = kyd; par[7] = sy0d;
+        par[8] = sz0d; par[9] = inv_s0d; par[10] = A_ln; par[11] = sM0; par[12] = Kck; par[13] = x0v; par[14] = inv_x0v;
+        par[15] = kyv; par[16] = sy0v; par[17] = near_s; par[18] = ctc; par[19] = watK; par[20] = reach1; par[21] = reach0;
+        par[22] = 0.0; par[23] = 0.0;
+        if (W > 1) {  // publish (the TI-dependent ones differ between the lateral columns: lanes 0..2 hold columns 0..2), then
+                      // tell the workers that source i is ready (they wait on the same named barrier)
+            if (lane < 3) {
+                double2* d = (double2*)(sm.spar + ((i & 1) * 3 + lane) * kSrcPar);
+#pragma unroll
+                for (int q = 0; q < kSrcPar / 2; ++q) d[q] = make_double2(par[2 * q], par[2 * q + 1]);
+            }
+            __threadfence_block();
+            __syncwarp();
+            bar_arrive<1>(i, NT);
+        }
+        } else {
+            bar_sync<1>(i, NT);
+            const double2* d = (const double2*)(sm.spar + ((i & 1) * 3 + j) * kSrcPar);
+#pragma unroll
+            for (int q = 0; q < kSrcPar / 2; ++q) { const double2 v = d[q]; par[2 * q] = v.x; par[2 * q + 1] = v.y; }
+        }
+        const double Gt = par[0], Gb = par[1], Gwr = par[2], x0d = par[3], inv_x0d = par[4], delta0 = par[5], kyd = par[6],
+                     sy0d = par[7], sz0d = par[8], inv_s0d = par[9], A_ln = par[10], sM0 = par[11], Kck = par[12], x0v = par[13],
+                     inv_x0v = par[14], kyv = par[15], sy0v = par[16], near_s = par[17], ctc = par[18],
+                     reach1 = par[20], reach0 = par[21];
+        double watK = par[19];  // (W > 1: the axial induction until a sweep needs the constant)
+        const double sz0v = fc.near_c * (0.5 / 0.501);
+        const uchar4 ixs = sm.idx[i];
+        const int lo = ixs.x, near_i = ixs.y, gt0_i = ixs.z, end15 = ixs.w;
+        const double x_i = __ldg(s.xi + row + i), y_i = __ldg(s.yi + row + i);  // block-uniform, L1-resident
 
         // --- transverse velocities of source i on the 3 vertical points of (target t, column j), evaluated directly
         auto v_direct = [&](const int t, const double dx, const double dyc, const bool active) {
@@ -635,28 +696,54 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             }
             __syncwarp();
         } else {
-            // ===== one fused pass: warp w takes targets t0 + 10 w .. t0 + 10 w + 9; the deficit part runs where some column
-            //       of the target is within reach of the wake =====
-#pragma unroll 1
-            for (int t0 = lo; t0 < T; t0 += kTurbPerPass * W) {
-                const int tr = t0 + kTurbPerPass * warp + g;
-                const bool active = lane_ok && tr < T && tr != i;
-                const int t = min(tr, T - 1);
+            // ===== W > 1, pipelined.  Source i + 1 needs, of source i's sweeps, only what lands on turbine i + 1; so the chain
+            //       warp applies source i to that one target itself and goes on to the prologue of source i + 1, while the
+            //       worker warps (1 .. W-1, ten targets each per pass) apply source i to the targets from i + 2 on (and to
+            //       x-tied predecessors), one source behind.  Named barriers 1, 2: "source ready" (chain arrives, workers
+            //       wait); 3, 4: "sweep done" (workers arrive, chain waits), alternating with the parity of i.  The chain warp
+            //       touches turbine i + 1 only after the workers' sweep of source i - 1 -- the last one that writes to it --
+            //       is done. =====
+            bool have_watK = false;
+            auto sweep = [&](const int tr, const bool on, const bool skip_vtab) {
+                const bool active = on && tr >= lo && tr < T && tr != i;
+                const int t = min(max(tr, 0), T - 1);
                 const double dx = sm.xs[t] - x_i;
                 const double dyc = __dsub_rn(__dadd_rn(sm.ys[t], offj), y_i);
                 const bool tab = vrow && t >= t_hi;
 #ifndef WF_DBG_SKIP_V  // timing experiment only
                 if (__any_sync(0xffffffffu, active && !tab)) v_direct(t, dx, dyc, active && !tab);
-                if (tab) v_table(t, active);
+                if (tab && !skip_vtab) v_table(t, active);
 #endif
                 const bool need = active && (t >= near_i) && (fabs(dyc) < reach(dx));
                 const unsigned nb = __ballot_sync(0xffffffffu, need);
 #ifndef WF_DBG_SKIP_D  // timing experiment only
-                if (nb) d_apply(t, dx, dyc, active && (((nb >> (3 * g)) & 7u) != 0u));
+                if (nb) {
+#ifndef WF_DBG_SKIP_POW
+                    if (!have_watK) { watK = fc.ch_const * exp(fc.ch_ai * log(watK)) * I0p; have_watK = true; }
 #endif
+                    d_apply(t, dx, dyc, active && (((nb >> (3 * g)) & 7u) != 0u));
+                }
+#endif
+            };
+            if (warp == 0) {
+                if (i > 0) bar_sync<3>(i - 1, NT);
+                if (i + 1 < T) sweep(i + 1, lane < 3, next_tab);  // (its table part is deferred to the next prologue)
+                __syncwarp();
+                near_gt = Gt; near_gwr = Gwr; near_c0 = next_c0; near_c1 = next_c1; near_tab = next_tab;
+            } else {
+#pragma unroll 1
+                for (int t0 = lo; t0 < i; t0 += kTurbPerPass * (W - 1))  // x-tied predecessors (none without ties: lo >= i)
+                    sweep(min(t0 + kTurbPerPass * (warp - 1) + g, i), lane_ok, false);
+#pragma unroll 1
+                for (int t0 = i + 2; t0 < T; t0 += kTurbPerPass * (W - 1)) sweep(t0 + kTurbPerPass * (warp - 1) + g, lane_ok, false);
+                __threadfence_block();
+                bar_arrive<3>(i, NT);
             }
-            __syncthreads();
         }
+    }
+    if (W > 1) {
+        if (warp == 0) bar_sync<3>(T - 1, NT);  // the workers' last sweep
+        __syncthreads();
     }
 
     // ---- epilogue (first warp) ------------------------------------------------------------------------------------------
