@@ -59,12 +59,19 @@ template <int BASE> __device__ __forceinline__ void bar_sync(int parity, int cou
 // division / sqrt / cbrt (IEEE rounding, full range, special cases) are 15-50 dependent instructions each.  The quantities
 // in the chain are positive, finite and far inside the float range, and the kernels owe 1e-9, not the last bit: seed with the
 // single-precision special-function unit and refine with Newton steps in double (error ~1e-15, a quarter of the instructions).
+#ifndef WF_LEAN_NEWTON
+#define WF_LEAN_NEWTON 2  // Newton steps after the single-precision seed.  1 was measured (profiles/r2_exp_newton.log): +2.8 % on
+                          // the FP64 step kernels, +0.5 % on the strict FP32 step, FP64 parity max 1.1e-12 -> 5.9e-11 (median
+                          // 3e-16 -> 5e-15); the bit-check mode keeps the margin
+#endif
 __device__ __forceinline__ double rcp64(double b) {
     float rf;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)b));
     double r = (double)rf;
     r = fma(r, fma(-b, r, 1.0), r);  // 6e-8 -> 4e-15
+#if WF_LEAN_NEWTON > 1
     r = fma(r, fma(-b, r, 1.0), r);  // -> rounding
+#endif
     return r;
 }
 __device__ __forceinline__ double sqrt64(double x) {  // x > 0
@@ -73,7 +80,9 @@ __device__ __forceinline__ double sqrt64(double x) {  // x > 0
     const double r = (double)rf, h = 0.5 * r;
     double y = x * r;
     y = fma(h, fma(-y, y, x), y);  // 1e-7 -> 1e-14
+#if WF_LEAN_NEWTON > 1
     y = fma(h, fma(-y, y, x), y);
+#endif
     return y;
 }
 __device__ __forceinline__ double sqrt64z(double x) { return x > 1e-30 ? sqrt64(x) : sqrt(x); }  // x >= 0, possibly tiny
@@ -83,7 +92,9 @@ __device__ __forceinline__ double cbrt64(double x) {  // x > 0
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)(3.0 * y0 * y0)));
     const double rc = (double)rf;
     double y = fma(fma(-y0 * y0, y0, x), rc, y0);  // Newton on y^3 = x with a single-precision slope: 1e-7 -> 1e-14
+#if WF_LEAN_NEWTON > 1
     y = fma(fma(-y * y, y, x), rc, y);
+#endif
     return y;
 }
 
