@@ -18,6 +18,7 @@
 #include "wf_reset_device.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #ifndef WF_VTAB64_PF_DIST
 #define WF_VTAB64_PF_DIST 1  // table rows of source i + 1 are prefetched to L2 while source i is processed (2: -4 %, 4: -8 %)
@@ -939,6 +940,8 @@ cudaError_t wf_launch_fixup64(int mode, bool use_vtab, const WfModel& m, const W
     int w = m.T > 40 ? 8 : (m.T > 20 ? 4 : (m.T > 10 ? 2 : 1));
     const int expected = env_count / 64 + 1;  // ~1.5 % of the envs
     while (w > 1 && expected > 148 * 8 / w) w >>= 1;
+    static const int forced = getenv("WFCRL_B200_FIX_WARPS") ? atoi(getenv("WFCRL_B200_FIX_WARPS")) : 0;  // tuning experiments
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) w = forced;
     const int resident = 148 * 8 / w;  // two ~196-register warps per SM sub-partition = 8 warps per SM
     const int grid = env_count < resident ? env_count : resident;
     switch (w) {
