@@ -463,6 +463,7 @@ __device__ __forceinline__ void solve_env64(const int b, const int mode, const b
             __syncwarp();  // every reader of this turbine's (v, w) above is done
             if (tid < 9) vw_st(9 * i + tid, make_double2(vq + Vs, wwq + Ws));
         } else if (GATHER || (W > 1 && near_tab)) {
+            __syncwarp();
             if (tid < 9) vw_st(9 * i + tid, make_double2(vq, wwq));
         }
         if (GATHER && tid == 0) sm.gg[i] = make_double2(Gt, Gwr);
