@@ -1,16 +1,24 @@
-// FP64 instantiation of the warp-per-env design (bit-check mode at speed): ONE WARP = ONE CTA = ONE ENVIRONMENT.
+// FP64 instantiations of the warp-per-env design: the bit-check mode at speed, and the re-solve of the envs a strict FP32
+// launch flagged.  One template (solve_env64<W, OutT, FIX, GATHER>), three kernels:
 //
-// Same structure as wf_fast.cu -- solver state in shared memory, warp-uniform source prologue, a vortex sweep over all
-// downstream targets and a compacted deficit sweep, 10 turbines x 3 lateral grid columns per pass -- but everything is
-// evaluated in double precision with the accurate CUDA math functions, and every simplification that would be visible
-// at the 1e-9 level is dropped:
+//   wf_step_fast64_kernel<true>   one warp = one CTA = one env, GATHER form: the transverse velocities of a turbine are summed
+//                                 from the target-major vortex-table rows when the turbine becomes the source (shared memory
+//                                 15 KB per 80-turbine env, 128 registers -> 14-16 envs per SM);
+//   wf_step_fast64_kernel<false>  the same warp-per-env solve in scatter form (V sweep over all downstream targets, compacted
+//                                 deficit queue) for handles without a vortex table;
+//   wf_fixup64_kernel<W>          W warps per env, built for latency: a chain warp evaluates the sources' scalar chains back to
+//                                 back while W-1 worker warps apply the previous source to its targets (named barriers).
+//
+// Everything is evaluated in double precision and every simplification of wf_fast.cu that would be visible at the 1e-9 level
+// is dropped:
 //   * positions are the FP64 rotated coordinates and the numpy-order means x_i, y_i of the geometry kernel;
 //   * the ground-mirror vortices keep their exp(-r/eps^2) core factor;
 //   * the deficit cut-off is 9.5 sigma (exp(-45) = 2.9e-20);
 //   * x-direction masks come from the geometry kernel's FP64 index table (bit-exact).
 // Algebra that only changes results at the rounding level (1e-16) is kept: exp(-(y^2+z^2)/eps^2) factorisation, paired
 // reciprocals, uR/(U0+u0) = 1/2, per-model grid integrals, sum of squares instead of the hypot chain, running maximum of
-// the wake-added TI.  Parity vs the oracle: <= 1e-9 relative (tests/test_solve_parity_gpu.py, test_env_parity_gpu.py).
+// the wake-added TI, Newton-refined reciprocals / square roots / cube roots seeded in single precision.
+// Parity vs the oracle: <= 1e-9 relative (tests/test_solve_parity_gpu.py, test_env_parity_gpu.py; measured max 1.1e-12).
 //
 // Algorithm: SURVEY.md Appendix A; reference call sites wfcrl/interface.py:557-586, 622-648; env semantics
 // wfcrl/mdp.py:273-319, wfcrl/simple_env.py:58-96, wfcrl/multiagent_env.py:198-249, wfcrl/rewards.py:16-46.
@@ -180,8 +188,9 @@ __device__ __forceinline__ void load_row12(const double* __restrict__ p, double*
 }
 // One env solved in FP64 by W warps (a CTA of 32 W threads).
 //   W = 1: the throughput configuration of the bit-check mode (one warp = one CTA = one env, compacted deficit queue).
-//   W > 1: the low-latency configuration used to re-solve the envs an FP32 launch flagged: every warp evaluates the source's
-//          scalar chain itself (no broadcast), then the W warps share the targets of ONE fused vortex + deficit pass.
+//   W > 1: the low-latency configuration used to re-solve the envs an FP32 launch flagged: warp 0 evaluates the sources'
+//          scalar chains and applies each source to the NEXT turbine itself; warps 1 .. W-1 apply it to all other targets
+//          one source behind (see the W > 1 branch of the source loop).
 // GATHER (W = 1 with a target-major vortex table): the (v, w) of a turbine are not accumulated in shared memory while the
 //          upstream sources are processed but summed from the table rows (j, i), j < i, in the prologue of source i, with the
 //          circulations (Gt, Gwr) of the earlier sources kept in shared memory (16 bytes per turbine instead of 144); the
