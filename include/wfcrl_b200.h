@@ -231,6 +231,14 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
                    int32_t* regs_per_thread, int32_t* threads_per_cta, int32_t* smem_per_cta);
 /* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 uint64_t wf_launch_count(WfHandle h);
+/* Per-kernel device timing of the step calls (wf_step / wf_update_command on device buffers), for bench.py's roofline block:
+ * while enabled, every step call brackets its step-kernel launch and -- on a strict FP32 handle -- its FP64 re-solve launch
+ * with CUDA events on the caller's stream (and waits for the PREVIOUS call's events, so it is for measurement legs, not for
+ * production loops).  wf_get_kernel_timing waits for the last call, returns the average duration of each launch over the
+ * calls since the previous query (resolve_ms = 0 where there is no second launch) and their number, and restarts the
+ * averages.  No reference counterpart (profiling hook). */
+int wf_set_kernel_timing(WfHandle h, int32_t enabled);
+int wf_get_kernel_timing(WfHandle h, double* step_kernel_ms, double* resolve_kernel_ms, int32_t* calls);
 
 const char* wf_last_error(void);
 const char* wf_version(void);

@@ -56,6 +56,8 @@ SYMBOLS = {
     "wf_reset_sampled": (C.c_int, [_P, _P, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int32, C.POINTER(WfStepOut), _P]),
     "wf_set_autoreset": (C.c_int, [_P, C.c_int32, C.c_uint64, C.c_int64, C.c_double, C.c_double]),
     "wf_autoreset_finish": (C.c_int, [_P, C.c_int32, C.POINTER(WfStepOut), _P]),
+    "wf_set_kernel_timing": (C.c_int, [_P, C.c_int32]),
+    "wf_get_kernel_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "wf_step": (C.c_int, [_P, _P, C.POINTER(WfStepOut), _P]),
     "wf_update_command": (C.c_int, [_P, _P, C.POINTER(WfStepOut), _P]),
     "wf_step_host": (C.c_int, [_P, _P, C.POINTER(WfStepOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -284,3 +284,14 @@ class FlorisBatch:
 
     def launch_count(self) -> int:
         return int(self.lib.wf_launch_count(self.handle))
+
+    def set_kernel_timing(self, enabled: bool):
+        """Bracket the launches of every following ``step`` / ``update_command`` with CUDA events (measurement legs only)."""
+        _lib.check(self.lib.wf_set_kernel_timing(self.handle, int(bool(enabled))))
+
+    def kernel_timing(self) -> Dict[str, float]:
+        """Average device time of the step kernel and of the FP64 re-solve kernel (0 where there is none) over the calls
+        since the last query, and their number."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        _lib.check(self.lib.wf_get_kernel_timing(self.handle, C.byref(a), C.byref(b), C.byref(n)))
+        return {"step_kernel_ms": a.value, "resolve_kernel_ms": b.value, "calls": n.value}

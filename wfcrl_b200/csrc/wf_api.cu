@@ -62,6 +62,11 @@ struct WfHandle_t {
     cudaEvent_t ev_chunk[kHostStreams] = {};
     bool fast_uses_vtab = false;  // FP32 step kernel reads the vortex table (off by default: measured slower than direct)
     bool vtab_stale = false;  // some env's vortex-table rows do not match its geometry: launch the kernels that ignore the table
+    // wf_set_kernel_timing: events around the step-kernel launch and the re-solve launch of the last step call
+    bool timing = false, timing_pending = false;
+    cudaEvent_t ev_t[3] = {};
+    double t_step_ms = 0.0, t_fix_ms = 0.0;
+    int t_calls = 0;
     uint64_t steps_since_wind_update = 1u << 30;  // wf_update_wind rebuilds the vortex table only when it is not called every step
 };
 
@@ -131,6 +136,8 @@ int wf_destroy(WfHandle h) {
     for (cudaStream_t st : h->host_streams)
         if (st) cudaStreamDestroy(st);
     if (h->ev_async) cudaEventDestroy(h->ev_async);
+    for (cudaEvent_t ev : h->ev_t)
+        if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_chunk)
         if (ev) cudaEventDestroy(ev);
     if (h->h_fix_rec) cudaFreeHost(h->h_fix_rec);
@@ -332,10 +339,39 @@ static int launch_fixup(WfHandle h, int mode, const WfOutPtrs& out, cudaStream_t
     return WF_OK;
 }
 
+// kernel timing (wf_set_kernel_timing): fold the previous call's events into the averages
+static void timing_collect(WfHandle h) {
+    if (!h->timing_pending) return;
+    h->timing_pending = false;
+    float a = 0.f, b = 0.f;
+    if (cudaEventSynchronize(h->ev_t[2]) != cudaSuccess || cudaEventElapsedTime(&a, h->ev_t[0], h->ev_t[1]) != cudaSuccess ||
+        cudaEventElapsedTime(&b, h->ev_t[1], h->ev_t[2]) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    h->t_step_ms += a;
+    h->t_fix_ms += b;
+    h->t_calls += 1;
+}
+
 static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float* d_action, const double* d_yaw,
                        const WfOutPtrs& out, cudaStream_t st, int env_begin = 0, int env_count = -1,
                        bool defer_fixup = false) {
     if (env_count < 0) env_count = h->model.B;
+    const bool timed = h->timing && !defer_fixup && env_begin == 0 && env_count == h->model.B;
+    if (timed) {
+        timing_collect(h);
+        cudaEventRecord(h->ev_t[0], st);
+    }
+    struct TimingTail {  // records the closing events on every return path
+        WfHandle h; cudaStream_t st; bool on, mid = false;
+        ~TimingTail() {
+            if (!on) return;
+            if (!mid) cudaEventRecord(h->ev_t[1], st);
+            cudaEventRecord(h->ev_t[2], st);
+            h->timing_pending = true;
+        }
+    } tail{h, st, timed};
     cudaError_t e;
     if (h->cfg.kernel == WF_KERNEL_FAST && h->cfg.precision == WF_PREC_F64)
         e = wf_launch_step_fast64(mode, !h->vtab_stale, h->model, h->fast64, h->st, d_mask, d_action, d_yaw, out, env_begin, env_count, st);
@@ -344,6 +380,7 @@ static int launch_step(WfHandle h, int mode, const uint8_t* d_mask, const float*
         e = wf_launch_step_fast(mode, h->fast_baked, h->fast_uses_vtab && !h->vtab_stale, h->model, h->fast, h->st, d_mask, d_action, d_yaw, out, env_begin,
                                 env_count, 0, st);
         if (e == cudaSuccess && is_strict_f32(h) && !defer_fixup) {  // strict FP32: FP64 re-solve of whatever the launch flagged
+            if (timed) { cudaEventRecord(h->ev_t[1], st); tail.mid = true; }
             h->launches += 1;
             h->steps_since_wind_update += 1;
             return launch_fixup(h, mode, out, st);
@@ -708,5 +745,31 @@ int wf_device_info(WfHandle h, int32_t* sm_count, int32_t* sm_clock_khz, int32_t
 }
 
 uint64_t wf_launch_count(WfHandle h) { return h ? h->launches : 0; }
+
+int wf_set_kernel_timing(WfHandle h, int32_t enabled) {
+    if (!h) return set_err(WF_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (enabled) {
+        for (cudaEvent_t& ev : h->ev_t)
+            if (!ev) CUDA_TRY(cudaEventCreate(&ev));
+    } else {
+        timing_collect(h);
+    }
+    h->timing = enabled != 0;
+    return WF_OK;
+}
+
+int wf_get_kernel_timing(WfHandle h, double* step_kernel_ms, double* resolve_kernel_ms, int32_t* calls) {
+    if (!h) return set_err(WF_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    timing_collect(h);
+    const int n = h->t_calls;
+    if (step_kernel_ms) *step_kernel_ms = n ? h->t_step_ms / n : 0.0;
+    if (resolve_kernel_ms) *resolve_kernel_ms = n ? h->t_fix_ms / n : 0.0;
+    if (calls) *calls = n;
+    h->t_step_ms = h->t_fix_ms = 0.0;
+    h->t_calls = 0;
+    return WF_OK;
+}
 
 }  // extern "C"
