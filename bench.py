@@ -596,7 +596,10 @@ def run_ours(args):
                           "instructions actually issued" + ("" if lanes == 128 else "; every special function counted as ONE "
                           "op although FP64 evaluates it in software (10-40 instructions), so this fraction is a lower bound"),
             "mufu": {"achieved": mufu_ach / 1e9, "peak": mufu_peak / 1e9, "frac": mufu_ach / mufu_peak,
-                     "unit": "G special/s"} if precision == "f32" else None,  # FP64 specials run on the FP64 pipe
+                     "unit": "G special/s",
+                     "note": "CANONICAL special-function count of Appendix A per env-step; the kernel shares reciprocals and "
+                             "exponentials and issues ~2.4x fewer MUFU instructions (ncu XU pipe ~51 % busy), so a value "
+                             "above 1 is not a measurement error"} if precision == "f32" else None,  # FP64 specials run on the FP64 pipe
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "frac": hbm_ach / hbm_peak, "unit": "GB/s",
                     "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
             "traffic": _ncu_traffic(("fast64" if precision == "f64" else "fast") if args.kernel == "fast" else
